@@ -1,0 +1,59 @@
+// Library-level entry points + shared host-side validation.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace advs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int validate_conv(const advs_conv_params* p, const char* who) {
+  ADVS_CHECK_ARG(p != nullptr, "%s: null params", who);
+  ADVS_CHECK_ARG(p->B > 0 && p->H > 0 && p->W > 0 && p->Cout > 0, "%s: bad output shape", who);
+  ADVS_CHECK_ARG(p->stride == 1 || p->stride == 2, "%s: stride must be 1 or 2", who);
+  ADVS_CHECK_ARG(p->nseg >= 1 && p->nseg <= 3, "%s: nseg must be 1..3", who);
+  for (int s = 0; s < p->nseg; ++s) {
+    ADVS_CHECK_ARG(p->seg[s].x && p->seg[s].w, "%s: segment %d has null pointers", who, s);
+    ADVS_CHECK_ARG(p->seg[s].taps == 9 || p->seg[s].taps == 1, "%s: taps must be 9 or 1", who);
+    ADVS_CHECK_ARG(p->seg[s].C > 0 && p->seg[s].C % 4 == 0, "%s: C must be a multiple of 4", who);
+    ADVS_CHECK_ARG(s == 0 || p->seg[s].taps == 1, "%s: shortcut segments must be 1x1", who);
+  }
+  ADVS_CHECK_ARG(p->stride == 1 || p->seg[0].taps == 9, "%s: stride 2 needs a 3x3 kernel", who);
+  ADVS_CHECK_ARG(p->dtype == ADVS_F32 || p->dtype == ADVS_BF16, "%s: bad dtype", who);
+  if (p->out_mode == 0) {
+    ADVS_CHECK_ARG(p->y != nullptr, "%s: y is null", who);
+  } else if (p->out_mode == 1) {
+    ADVS_CHECK_ARG(p->q && p->k && p->vt, "%s: q/k/vt null in qkv mode", who);
+    ADVS_CHECK_ARG(p->heads > 0 && p->Cout % (3 * p->heads) == 0, "%s: Cout not 3*heads*dh", who);
+    ADVS_CHECK_ARG(p->residual == nullptr, "%s: residual unsupported in qkv mode", who);
+  } else {
+    ADVS_CHECK_ARG(false, "%s: bad out_mode", who);
+  }
+  return ADVS_OK;
+}
+
+}  // namespace advs
+
+extern "C" {
+
+int advs_version(void) { return 100; }
+
+const char* advs_last_error(void) { return advs::g_err; }
+
+int advs_device_is_sm100(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+}  // extern "C"

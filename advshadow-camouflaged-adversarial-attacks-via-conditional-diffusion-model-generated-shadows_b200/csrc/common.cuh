@@ -1,0 +1,131 @@
+// Shared helpers for the advshadow_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "advshadow_b200.h"
+
+namespace advs {
+
+void set_error(const char* fmt, ...);
+
+#define ADVS_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      advs::set_error(__VA_ARGS__);    \
+      return ADVS_ERR_ARG;             \
+    }                                  \
+  } while (0)
+
+#define ADVS_CHECK_LAUNCH(name)                                                   \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      advs::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return ADVS_ERR_CUDA;                                                       \
+    }                                                                             \
+  } while (0)
+
+// ---- storage-type helpers -------------------------------------------------------------
+template <typename T> struct Vec8;  // 8 consecutive elements
+template <> struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void to_float(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ __forceinline__ void from_float(const float* f) {
+    a = make_float4(f[0], f[1], f[2], f[3]);
+    b = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ __forceinline__ void to_float(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void from_float(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// accurate variant (fp32 parity mode): expf instead of the fast intrinsic
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- fused conv epilogue shared by the SIMT and the tcgen05 kernels ---------------------
+struct EpilogueParams {
+  const float* bias;
+  const float* temb;
+  int temb_stride;
+  int out_mode;
+  const void* residual;
+  void* y;
+  void* q;
+  void* k;
+  void* vt;
+  int heads;
+  int dh;
+  float qk_scale;
+  int HW;    // pixels per image (T for attention)
+  int Cout;
+};
+
+inline EpilogueParams make_epilogue(const advs_conv_params& p) {
+  EpilogueParams e;
+  e.bias = p.bias;
+  e.temb = p.temb;
+  e.temb_stride = p.temb_stride;
+  e.out_mode = p.out_mode;
+  e.residual = p.residual;
+  e.y = p.y;
+  e.q = p.q;
+  e.k = p.k;
+  e.vt = p.vt;
+  e.heads = p.heads > 0 ? p.heads : 1;
+  e.dh = p.out_mode == 1 ? p.Cout / (3 * e.heads) : 0;
+  e.qk_scale = p.qk_scale;
+  e.HW = p.H * p.W;
+  e.Cout = p.Cout;
+  return e;
+}
+
+int validate_conv(const advs_conv_params* p, const char* who);
+
+}  // namespace advs

@@ -1,0 +1,467 @@
+// K1/K2/K3: convolution as a persistent, warp-specialised implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[128 pixels, BN couts] (fp32, TMEM) += A[128 pixels, 64 ch] (bf16, smem) * W[BN couts, 64 ch]^T
+//
+// * activations are NHWC bf16; one TMA 4-D box {64 ch, tw, th, tn} per (tap, channel block) lands a
+//   128-row K-major SWIZZLE_128B tile -- the 3x3 taps are just shifted box coordinates and the
+//   zero padding is TMA's out-of-bounds fill, so no im2col buffer ever exists;
+// * stride-2 convolutions read four "parity" views of the input (even/odd rows x even/odd columns);
+// * ResidualBlock's 1x1 shortcut conv (and the two halves of a virtual concat) are extra K-segments
+//   accumulated into the same TMEM tile;
+// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-5 = epilogue (TMEM -> registers ->
+//   bias / time-embedding / residual -> bf16 -> global).  TMEM holds two accumulator tiles so the
+//   epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Reference ops replaced: nn.Conv2d at dm1:73, 86, 90, 114-115, 134, 148 (+ the adds at dm1:101,103,127).
+#include <string.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace advs {
+
+using namespace sm100;
+
+struct ConvMaps {
+  CUtensorMap a[6];  // [0..3] segment 0 (stride 1: only [0]; stride 2: parity hp*2+wp), [4],[5] segments 1,2
+  CUtensorMap b[3];
+};
+
+struct ConvArgs {
+  int B, H, W, Cout;
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_n, m_tiles, n_tiles;
+  int stride, nseg;
+  int taps[3], cblks[3];
+  int total_kb;
+  uint32_t a_bytes;
+  EpilogueParams epi;
+};
+
+struct ConvPlan {
+  ConvMaps maps;
+  ConvArgs args;
+  int bn;
+  int grid;
+  uint32_t smem_bytes;
+  uint32_t magic;
+};
+static_assert(sizeof(ConvPlan) <= ADVS_CONV_PLAN_BYTES, "ConvPlan does not fit ADVS_CONV_PLAN_BYTES");
+
+constexpr int kConvThreads = 192;
+constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+template <int BN>
+struct ConvCfg {
+  static constexpr uint32_t b_bytes = BN * 128;
+  static constexpr uint32_t stage_bytes = kABytes + b_bytes;
+  static constexpr int stages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t bar_bytes = 256;
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + bar_bytes + 1024;  // + alignment slack
+  static constexpr uint32_t tmem_cols = 2 * BN;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 32 consecutive output channels [n, n+32) of one pixel row
+__device__ __forceinline__ void epilogue_store32(const EpilogueParams& e, const uint32_t* acc, size_t m, int b, int t,
+                                                 int n) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (e.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t4 = __ldg(bp + j);
+      v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+    }
+  }
+  if (e.temb) {
+    const float4* tp = reinterpret_cast<const float4*>(e.temb + (size_t)b * e.temb_stride + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t4 = __ldg(tp + j);
+      v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+    }
+  }
+  if (e.out_mode == 0) {
+    if (e.residual) {
+      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.Cout + n);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 r4 = __ldg(rp + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 f = __bfloat1622float2(h[i]);
+          v[8 * j + 2 * i] += f.x;
+          v[8 * j + 2 * i + 1] += f.y;
+        }
+      }
+    }
+    uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+      o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+      o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      yp[j] = o;
+    }
+  } else {
+    const int head = n / (3 * e.dh);
+    const int r = n - head * 3 * e.dh;
+    const int which = r / e.dh;
+    const int d0 = r - which * e.dh;
+    const size_t bh = (size_t)b * e.heads + head;
+    if (which < 2) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh + d0;
+      uint4* yp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * j] * e.qk_scale, v[8 * j + 1] * e.qk_scale);
+        o.y = pack_bf16x2(v[8 * j + 2] * e.qk_scale, v[8 * j + 3] * e.qk_scale);
+        o.z = pack_bf16x2(v[8 * j + 4] * e.qk_scale, v[8 * j + 5] * e.qk_scale);
+        o.w = pack_bf16x2(v[8 * j + 6] * e.qk_scale, v[8 * j + 7] * e.qk_scale);
+        yp[j] = o;
+      }
+    } else {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh + d0) * e.HW + t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[(size_t)j * e.HW] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kConvThreads, 1)
+k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int STAGES = Cfg::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 6; ++i) tma_prefetch_desc(&maps.a[i]);
+    for (int i = 0; i < 3; ++i) tma_prefetch_desc(&maps.b[i]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::tmem_cols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+        const int w0 = (m_tile % a.tiles_w) * a.tw;
+        const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.th;
+        const int n0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.tn;
+        const int nb = n_tile * BN;
+        for (int s = 0; s < a.nseg; ++s) {
+          const int taps = a.taps[s];
+          for (int tap = 0; tap < taps; ++tap) {
+            const CUtensorMap* amap;
+            int cw = w0, ch = h0;
+            if (taps == 9) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              if (s == 0 && a.stride == 2) {
+                amap = &maps.a[(dy != 1 ? 2 : 0) + (dx != 1 ? 1 : 0)];
+                ch += (dy == 0) ? -1 : 0;
+                cw += (dx == 0) ? -1 : 0;
+              } else {
+                amap = &maps.a[s == 0 ? 0 : 3 + s];
+                ch += dy - 1;
+                cw += dx - 1;
+              }
+            } else {
+              amap = &maps.a[s == 0 ? 0 : 3 + s];
+            }
+            for (int cb = 0; cb < a.cblks[s]; ++cb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * Cfg::stage_bytes;
+              mbar_arrive_expect_tx(&full[stage], a.a_bytes + Cfg::b_bytes);
+              tma_load_4d(sa, amap, &full[stage], cb * 64, cw, ch, n0);
+              tma_load_3d(sa + kABytes, &maps.b[s], &full[stage], cb * 64, tap, nb);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < a.total_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) per 64-channel block
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int rows_valid = a.tw * a.th * a.tn;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+      const int w0 = (m_tile % a.tiles_w) * a.tw;
+      const int h0 = ((m_tile / a.tiles_w) % a.tiles_h) * a.th;
+      const int n0 = (m_tile / (a.tiles_w * a.tiles_h)) * a.tn;
+      const int dn = row / (a.th * a.tw);
+      const int rem = row - dn * (a.th * a.tw);
+      const int dh = rem / a.tw, dw = rem - dh * a.tw;
+      const int b = n0 + dn;
+      const bool valid = row < rows_valid && b < a.B;
+      const int t = (h0 + dh) * a.W + (w0 + dw);
+      const size_t m = (size_t)b * a.epi.HW + t;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + chunk * 32, r);
+        tmem_wait_ld();
+        const int n = n_tile * BN + chunk * 32;
+        if (valid && n < a.Cout) epilogue_store32(a.epi, r, m, b, t, n);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::tmem_cols>(tmem_base);
+}
+
+// ---- host ------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int encode_bf16_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const char* who) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("%s: cuTensorMapEncodeTiled not available (no CUDA driver?)", who);
+    return ADVS_ERR_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", who,
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return ADVS_ERR_CUDA;
+  }
+  return ADVS_OK;
+}
+
+static int largest_divisor_leq(int n, int cap) {
+  int best = 1;
+  for (int d = 1; d <= cap && d <= n; ++d)
+    if (n % d == 0) best = d;
+  return best;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace advs
+
+using namespace advs;
+
+extern "C" {
+
+int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
+  int rc = validate_conv(p, "conv_sm100_plan");
+  if (rc) return rc;
+  ADVS_CHECK_ARG(plan_host && ((uintptr_t)plan_host % 64) == 0, "conv_sm100_plan: plan buffer must be 64-byte aligned");
+  ADVS_CHECK_ARG(p->dtype == ADVS_BF16, "conv_sm100_plan: bf16 only");
+  ADVS_CHECK_ARG(p->Cout % 64 == 0, "conv_sm100_plan: Cout must be a multiple of 64");
+  for (int s = 0; s < p->nseg; ++s)
+    ADVS_CHECK_ARG(p->seg[s].C % 64 == 0, "conv_sm100_plan: segment channels must be multiples of 64");
+  if (p->out_mode == 1) {
+    int dh = p->Cout / (3 * p->heads);
+    ADVS_CHECK_ARG(dh % 32 == 0, "conv_sm100_plan: head dim must be a multiple of 32");
+  }
+  ADVS_CHECK_ARG(!p->bias || ((uintptr_t)p->bias % 16) == 0, "conv_sm100_plan: bias must be 16-byte aligned");
+  ADVS_CHECK_ARG(!p->temb || (((uintptr_t)p->temb % 16) == 0 && p->temb_stride % 4 == 0),
+                 "conv_sm100_plan: temb must be 16-byte aligned with stride%%4==0");
+
+  ConvPlan* plan = reinterpret_cast<ConvPlan*>(plan_host);
+  memset(plan, 0, sizeof(ConvPlan));
+  ConvArgs& a = plan->args;
+  a.B = p->B; a.H = p->H; a.W = p->W; a.Cout = p->Cout;
+  a.stride = p->stride; a.nseg = p->nseg;
+  a.tw = largest_divisor_leq(p->W, 128);
+  a.th = largest_divisor_leq(p->H, 128 / a.tw);
+  a.tn = 1;
+  if (a.th == p->H && a.tw == p->W) {
+    a.tn = 128 / (a.tw * a.th);
+    if (a.tn > p->B) a.tn = p->B;
+    if (a.tn < 1) a.tn = 1;
+  }
+  a.tiles_w = p->W / a.tw;
+  a.tiles_h = p->H / a.th;
+  a.tiles_n = (p->B + a.tn - 1) / a.tn;
+  a.m_tiles = a.tiles_w * a.tiles_h * a.tiles_n;
+  a.a_bytes = (uint32_t)(a.tw * a.th * a.tn) * 128u;
+  a.total_kb = 0;
+  for (int s = 0; s < 3; ++s) {
+    a.taps[s] = s < p->nseg ? p->seg[s].taps : 0;
+    a.cblks[s] = s < p->nseg ? p->seg[s].C / 64 : 0;
+    a.total_kb += a.taps[s] * a.cblks[s];
+  }
+  a.epi = make_epilogue(*p);
+
+  int bn = 128;
+  if (p->Cout % 256 == 0 && (long long)a.m_tiles * (p->Cout / 256) >= num_sms()) bn = 256;
+  plan->bn = bn;
+  a.n_tiles = (p->Cout + bn - 1) / bn;
+
+  // ---- TMA descriptors ----
+  const uint32_t abox[4] = {64u, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)a.tn};
+  for (int s = 0; s < p->nseg; ++s) {
+    const int C = p->seg[s].C;
+    const char* base = reinterpret_cast<const char*>(p->seg[s].x);
+    if (s == 0 && p->stride == 2) {
+      const int Hin = 2 * p->H, Win = 2 * p->W;
+      for (int hp = 0; hp < 2; ++hp)
+        for (int wp = 0; wp < 2; ++wp) {
+          uint64_t dims[4] = {(uint64_t)C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+          uint64_t str[4] = {2, (uint64_t)2 * C * 2, (uint64_t)2 * Win * C * 2, (uint64_t)Hin * Win * C * 2};
+          const char* b2 = base + ((size_t)hp * Win + wp) * C * 2;
+          rc = encode_bf16_map(&plan->maps.a[hp * 2 + wp], b2, 4, dims, str, abox, "conv_sm100_plan(A/stride2)");
+          if (rc) return rc;
+        }
+    } else {
+      uint64_t dims[4] = {(uint64_t)C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+      uint64_t str[4] = {2, (uint64_t)C * 2, (uint64_t)p->W * C * 2, (uint64_t)p->H * p->W * C * 2};
+      rc = encode_bf16_map(&plan->maps.a[s == 0 ? 0 : 3 + s], base, 4, dims, str, abox, "conv_sm100_plan(A)");
+      if (rc) return rc;
+    }
+    uint64_t wd[3] = {(uint64_t)C, (uint64_t)p->seg[s].taps, (uint64_t)p->Cout};
+    uint64_t ws[3] = {2, (uint64_t)C * 2, (uint64_t)p->seg[s].taps * C * 2};
+    const uint32_t wbox[3] = {64u, 1u, (uint32_t)bn};
+    rc = encode_bf16_map(&plan->maps.b[s], p->seg[s].w, 3, wd, ws, wbox, "conv_sm100_plan(W)");
+    if (rc) return rc;
+  }
+  // unused descriptor slots: replicate a valid one so prefetch.tensormap never sees garbage
+  for (int i = 0; i < 6; ++i) {
+    bool used = (i == 0) || (p->stride == 2 && i < 4) || (i >= 4 && (i - 3) < p->nseg);
+    if (!used) plan->maps.a[i] = plan->maps.a[0];
+  }
+  for (int i = p->nseg; i < 3; ++i) plan->maps.b[i] = plan->maps.b[0];
+
+  const int total_tiles = a.m_tiles * a.n_tiles;
+  plan->grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  plan->smem_bytes = bn == 256 ? ConvCfg<256>::smem_bytes : ConvCfg<128>::smem_bytes;
+  plan->magic = 0xC0A7B200u;
+  return ADVS_OK;
+}
+
+int advs_conv_sm100_launch(const void* plan_host, void* stream) {
+  const ConvPlan* plan = reinterpret_cast<const ConvPlan*>(plan_host);
+  ADVS_CHECK_ARG(plan && plan->magic == 0xC0A7B200u, "conv_sm100_launch: not a plan");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ConvCfg<128>::smem_bytes);
+    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ConvCfg<256>::smem_bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_error("conv_sm100_launch: cudaFuncSetAttribute failed: %s",
+                cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return ADVS_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  if (plan->bn == 256)
+    k_conv_sm100<256><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);
+  else
+    k_conv_sm100<128><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);
+  ADVS_CHECK_LAUNCH("conv_sm100_launch");
+  return ADVS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+// Fused convolution epilogue shared by the SIMT and tcgen05 implicit-GEMM kernels.
+//   v += bias[n] + temb[b, n] + residual[m, n]  ->  NHWC store, or the attention q/k/v^T split.
+#pragma once
+#include "common.cuh"
+
+namespace advs {
+
+// scalar path: one accumulator element (pixel m of image b at in-image index t, channel n)
+template <typename T>
+__device__ __forceinline__ void epilogue_store1(const EpilogueParams& e, size_t m, int b, int t, int n, float v) {
+  if (e.bias) v += e.bias[n];
+  if (e.temb) v += e.temb[(size_t)b * e.temb_stride + n];
+  if (e.out_mode == 0) {
+    if (e.residual) v += to_f(reinterpret_cast<const T*>(e.residual)[m * e.Cout + n]);
+    reinterpret_cast<T*>(e.y)[m * e.Cout + n] = from_f<T>(v);
+  } else {
+    int head = n / (3 * e.dh);
+    int r = n - head * 3 * e.dh;
+    int which = r / e.dh;
+    int d = r - which * e.dh;
+    size_t bh = (size_t)b * e.heads + head;
+    if (which == 0) reinterpret_cast<T*>(e.q)[(bh * e.HW + t) * e.dh + d] = from_f<T>(v * e.qk_scale);
+    else if (which == 1) reinterpret_cast<T*>(e.k)[(bh * e.HW + t) * e.dh + d] = from_f<T>(v * e.qk_scale);
+    else reinterpret_cast<T*>(e.vt)[(bh * e.dh + d) * e.HW + t] = from_f<T>(v);
+  }
+}
+
+}  // namespace advs

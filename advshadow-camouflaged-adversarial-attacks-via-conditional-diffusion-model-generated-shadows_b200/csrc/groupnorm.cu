@@ -1,0 +1,242 @@
+// K5: GroupNorm(G, C) [+ SiLU] over NHWC activations, optionally over the virtual concat of two
+// sources (reference: norm_layer dm1:62-63 used at dm1:71-72, 83-84, 113, 240-241; the concat is
+// torch.cat([h, hs.pop()], 1) at dm1:265).
+//
+// Three launches, all bandwidth-bound and deterministic (no float atomics):
+//   1. k_gn_partial : per (image, pixel-chunk, channel) sum / sum-of-squares        reads x once
+//   2. k_gn_finalize: per (image, group) mean/rstd in fp64 -> per-channel scale/shift (tiny)
+//   3. k_gn_apply   : y = act(x * scale + shift)                                    reads x, writes y
+// Algorithmic bytes: 2 reads + 1 write per element (6 B/elem bf16, 12 B/elem fp32).
+#include "common.cuh"
+
+namespace advs {
+
+struct GnGeom {
+  int chunks;          // pixel chunks per image
+  int pix_per_chunk;
+};
+
+static GnGeom gn_geom(int B, int HW) {
+  // aim for >= 4 CTAs per SM over the whole launch, chunks of at least 64 pixels
+  int want = (148 * 4 + B - 1) / B;
+  int max_chunks = (HW + 63) / 64;
+  int chunks = want < max_chunks ? want : max_chunks;
+  if (chunks < 1) chunks = 1;
+  GnGeom g;
+  g.pix_per_chunk = (HW + chunks - 1) / chunks;
+  g.chunks = (HW + g.pix_per_chunk - 1) / g.pix_per_chunk;
+  return g;
+}
+
+// part layout: [B][chunks][Ctot][2]
+template <typename T>
+__global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot, int HW, int pix_per_chunk,
+                             float* __restrict__ part) {
+  extern __shared__ float red[];  // [ppi][C]
+  const int cv = C / 8;
+  const int ppi = blockDim.x / cv;  // pixels per iteration (>= 1 by host check)
+  const int pl = threadIdx.x / cv;
+  const int j = threadIdx.x % cv;
+  const bool active = pl < ppi;
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int p0 = chunk * pix_per_chunk;
+  int p1 = p0 + pix_per_chunk;
+  if (p1 > HW) p1 = HW;
+
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+  if (active) {
+    const T* base = x + ((size_t)b * HW) * C + j * 8;
+    for (int p = p0 + pl; p < p1; p += ppi) {
+      Vec8<T> v;
+      v.load(base + (size_t)p * C);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        ss[i] = fmaf(f[i], f[i], ss[i]);
+      }
+    }
+  }
+  float* out = part + (((size_t)b * gridDim.x + chunk) * Ctot + c_off) * 2;
+  // pass 1: sums
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + j * 8 + i] = s[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < ppi; ++q) t += red[q * C + c];
+    out[c * 2] = t;
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + j * 8 + i] = ss[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < ppi; ++q) t += red[q * C + c];
+    out[c * 2 + 1] = t;
+  }
+}
+
+// one warp per (image, group)
+__global__ void k_gn_finalize(const float* __restrict__ part, int chunks, int Ctot, int groups, int HW, float eps,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ scale_shift, int B) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= B * groups) return;
+  int b = warp / groups, g = warp % groups;
+  int cpg = Ctot / groups;
+  double S = 0.0, SS = 0.0;
+  int n_items = chunks * cpg;
+  for (int it = lane; it < n_items; it += 32) {
+    int ch = it / cpg, c = g * cpg + it % cpg;
+    const float* p = part + (((size_t)b * chunks + ch) * Ctot + c) * 2;
+    S += (double)p[0];
+    SS += (double)p[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    SS += __shfl_xor_sync(0xffffffffu, SS, o);
+  }
+  double n = (double)HW * cpg;
+  double mean = S / n;
+  double var = SS / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  float meanf = (float)mean;
+  for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+    float sc = rstd * gamma[c];
+    float sh = beta[c] - meanf * sc;
+    scale_shift[((size_t)b * Ctot + c) * 2] = sc;
+    scale_shift[((size_t)b * Ctot + c) * 2 + 1] = sh;
+  }
+}
+
+template <typename T, bool SILU>
+__global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict__ x1, int c1, int HW, size_t npix,
+                           const float* __restrict__ scale_shift, T* __restrict__ y) {
+  const int Ctot = c0 + c1;
+  const int cv = Ctot / 8;
+  size_t total = npix * cv;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int j = (int)(idx % cv);
+    size_t p = idx / cv;
+    int b = (int)(p / HW);
+    int c = j * 8;
+    Vec8<T> v;
+    if (c < c0) v.load(x0 + p * c0 + c);
+    else v.load(x1 + p * c1 + (c - c0));
+    float f[8];
+    v.to_float(f);
+    const float4* ab = reinterpret_cast<const float4*>(scale_shift + ((size_t)b * Ctot + c) * 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 t = __ldg(ab + i);
+      float a = fmaf(f[2 * i], t.x, t.y);
+      float d = fmaf(f[2 * i + 1], t.z, t.w);
+      if (SILU) {
+        if constexpr (sizeof(T) == 4) { a = silu_acc(a); d = silu_acc(d); }
+        else { a = silu_f(a); d = silu_f(d); }
+      }
+      f[2 * i] = a;
+      f[2 * i + 1] = d;
+    }
+    v.from_float(f);
+    v.store(y + p * Ctot + c);
+  }
+}
+
+template <typename T>
+static int gn_stats_impl(const void* x0, int c0, const void* x1, int c1, int B, int HW, int groups, float eps,
+                         const float* gamma, const float* beta, float* scale_shift, void* ws, cudaStream_t st) {
+  GnGeom g = gn_geom(B, HW);
+  int Ctot = c0 + c1;
+  float* part = (float*)ws;
+  const void* xs[2] = {x0, x1};
+  int cs[2] = {c0, c1};
+  int off = 0;
+  for (int s = 0; s < 2; ++s) {
+    int C = cs[s];
+    if (C == 0) continue;
+    int cv = C / 8;
+    int threads = cv <= 256 ? 256 : 1024;
+    int ppi = threads / cv;
+    size_t smem = (size_t)ppi * C * sizeof(float);
+    dim3 grid(g.chunks, B);
+    k_gn_partial<T><<<grid, threads, smem, st>>>((const T*)xs[s], C, off, Ctot, HW, g.pix_per_chunk, part);
+    ADVS_CHECK_LAUNCH("groupnorm_stats/partial");
+    off += C;
+  }
+  int warps = B * groups;
+  k_gn_finalize<<<(warps * 32 + 127) / 128, 128, 0, st>>>(part, g.chunks, Ctot, groups, HW, eps, gamma, beta,
+                                                         scale_shift, B);
+  ADVS_CHECK_LAUNCH("groupnorm_stats/finalize");
+  return ADVS_OK;
+}
+
+template <typename T>
+static int gn_apply_impl(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* ss, int silu,
+                         void* y, cudaStream_t st) {
+  size_t npix = (size_t)B * HW;
+  size_t total = npix * ((c0 + c1) / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (silu)
+    k_gn_apply<T, true><<<(unsigned)blocks, 256, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, npix, ss, (T*)y);
+  else
+    k_gn_apply<T, false><<<(unsigned)blocks, 256, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, npix, ss, (T*)y);
+  ADVS_CHECK_LAUNCH("groupnorm_apply");
+  return ADVS_OK;
+}
+
+}  // namespace advs
+
+using namespace advs;
+
+extern "C" {
+
+size_t advs_groupnorm_workspace_bytes(int B, int HW, int C) {
+  if (B <= 0 || HW <= 0 || C <= 0) return 0;
+  GnGeom g = gn_geom(B, HW);
+  return (size_t)B * g.chunks * C * 2 * sizeof(float);
+}
+
+int advs_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int B, int HW, int groups, float eps,
+                         const float* gamma, const float* beta, float* scale_shift, void* workspace,
+                         size_t workspace_bytes, int dtype, void* stream) {
+  ADVS_CHECK_ARG(x0 && c0 > 0 && B > 0 && HW > 0 && groups > 0, "groupnorm_stats: bad args");
+  if (!x1) c1 = 0;
+  ADVS_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm_stats: channel counts must be multiples of 8");
+  ADVS_CHECK_ARG((c0 + c1) % groups == 0, "groupnorm_stats: channels not divisible by groups");
+  ADVS_CHECK_ARG(c0 / 8 <= 1024 && c1 / 8 <= 1024, "groupnorm_stats: at most 8192 channels per source");
+  ADVS_CHECK_ARG(gamma && beta && scale_shift && workspace, "groupnorm_stats: null pointer");
+  ADVS_CHECK_ARG(workspace_bytes >= advs_groupnorm_workspace_bytes(B, HW, c0 + c1), "groupnorm_stats: workspace too small");
+  if (dtype == ADVS_F32)
+    return gn_stats_impl<float>(x0, c0, x1, c1, B, HW, groups, eps, gamma, beta, scale_shift, workspace, (cudaStream_t)stream);
+  if (dtype == ADVS_BF16)
+    return gn_stats_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, groups, eps, gamma, beta, scale_shift, workspace, (cudaStream_t)stream);
+  ADVS_CHECK_ARG(false, "groupnorm_stats: bad dtype");
+}
+
+int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* scale_shift,
+                         int silu, void* y, int dtype, void* stream) {
+  ADVS_CHECK_ARG(x0 && c0 > 0 && B > 0 && HW > 0 && scale_shift && y, "groupnorm_apply: bad args");
+  if (!x1) c1 = 0;
+  ADVS_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm_apply: channel counts must be multiples of 8");
+  if (dtype == ADVS_F32) return gn_apply_impl<float>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
+  if (dtype == ADVS_BF16) return gn_apply_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
+  ADVS_CHECK_ARG(false, "groupnorm_apply: bad dtype");
+}
+
+}  // extern "C"

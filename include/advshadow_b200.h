@@ -1,0 +1,200 @@
+/*
+ * advshadow_b200 -- C ABI of the B200-native DDIM shadow sampler hot path.
+ *
+ * The reference (Raineasy/AdvShadow, pure Python/PyTorch) has no FFI of its own;
+ * its boundary is the Python surface of diff_model.py / ddim2/diff_model2.py.
+ * Each entry point below replaces one group of PyTorch calls on that surface and
+ * cites it (file:line relative to the reference root; dm1 = diff_model.py,
+ * dm2 = ddim2/diff_model2.py, ts = tools/train_shadow.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - no allocation, no synchronisation, no host callbacks inside any launch
+ *     function: all of them are CUDA-graph capturable; scratch memory is
+ *     supplied by the caller;
+ *   - return value 0 = ok, <0 = error (advs_last_error() gives the text);
+ *   - activations are NHWC ("pixel-major"): element (b,h,w,c) of a [B,H,W,C]
+ *     tensor lives at ((b*H+h)*W+w)*C+c.  Sampler state x_t / eps stay in the
+ *     reference's NCHW fp32 layout;
+ *   - `dtype`: ADVS_F32 (fp32 storage, SIMT fp32 math: the <=1e-4 mode) or
+ *     ADVS_BF16 (bf16 storage, fp32 accumulate: the throughput mode).
+ */
+#ifndef ADVSHADOW_B200_H
+#define ADVSHADOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADVS_F32 0
+#define ADVS_BF16 1
+
+#define ADVS_OK 0
+#define ADVS_ERR_ARG (-1)
+#define ADVS_ERR_CUDA (-2)
+#define ADVS_ERR_UNSUPPORTED (-3)
+
+/* ---- library ---------------------------------------------------------------------------- */
+int advs_version(void);
+const char* advs_last_error(void);
+/* 1 if the device behind the current context is compute capability 10.x */
+int advs_device_is_sm100(void);
+
+/* ---- K6: timestep embedding + small linears (dm1:16-33, dm1:184-188, dm1:77-80) ----------- */
+/* out[i, 0:half] = cos(t_i * f_j), out[i, half:2*half] = sin(t_i * f_j)  (dm1:25-30, "cos first").
+ * freqs[half] is the reference's table exp(-ln(max_period) * arange(half) / half); the reference
+ * always evaluates it on the host (dm1:25-28: torch.arange has no device argument) and uploads
+ * it, so the host side does the same and passes the device copy here. */
+int advs_timestep_embedding(const int64_t* t, int nt, const float* freqs, int half, float* out,
+                            void* stream);
+/* y[r, o] = act_out( sum_i act_in(x[r, i]) * w[o, i] + b[o] ), act = SiLU when the flag is set.
+ * Replaces nn.Linear / nn.SiLU in UNetModel.time_embed (dm1:184-188) and
+ * ResidualBlock.time_emb (dm1:77-80).  fp32 throughout. */
+int advs_linear_f32(const float* x, const float* w, const float* b, float* y, int rows, int in_f,
+                    int out_f, int silu_in, int silu_out, void* stream);
+
+/* ---- weight packing --------------------------------------------------------------------- */
+/* nn.Conv2d weight OIHW fp32 -> [O][kh*kw][I] in `dtype` (K-major rows for the implicit GEMM). */
+int advs_pack_conv_weight(const float* w_oihw, void* dst, int O, int I, int kh, int kw, int dtype,
+                          void* stream);
+
+/* ---- K1 edge layers: Cin=3 stem and Cout=3 head (dm1:192, dm1:240-242) -------------------- */
+/* x NCHW fp32 [B,Cin,H,W], w fp32 [Cout][9][Cin], y NHWC `dtype` [B,H,W,Cout]. 3x3, pad 1. */
+int advs_conv3x3_stem(const float* x_nchw, const float* w, const float* bias, void* y, int B,
+                      int H, int W, int Cin, int Cout, int dtype, void* stream);
+/* x NHWC `dtype` [B,H,W,Cin], w fp32 [Cout][9][Cin], y NCHW fp32 [B,Cout,H,W]. 3x3, pad 1. */
+int advs_conv3x3_head(const void* x, const float* w, const float* bias, float* y_nchw, int B,
+                      int H, int W, int Cin, int Cout, int dtype, void* stream);
+
+/* ---- K5: GroupNorm(32,C) [+ SiLU] over NHWC, optionally over a virtual concat of two
+ *      sources (dm1:62-63, 71-72, 83-84, 113, 240-241; torch.cat at dm1:265) ----------------- */
+/* scratch floats needed by advs_groupnorm_stats */
+size_t advs_groupnorm_workspace_bytes(int B, int HW, int C);
+/* per-(b,channel) affine  y = x*scale + shift  with scale = rstd*gamma, shift = beta-mean*rstd*gamma
+ * written to scale_shift[B][C][2].  x1 may be NULL (c1 = 0). */
+int advs_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int B, int HW, int groups,
+                         float eps, const float* gamma, const float* beta, float* scale_shift,
+                         void* workspace, size_t workspace_bytes, int dtype, void* stream);
+int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW,
+                         const float* scale_shift, int silu, void* y, int dtype, void* stream);
+
+/* ---- K1/K2/K3: convolution as implicit GEMM (dm1:73, 86, 90, 114-115, 134, 148) ----------- */
+/* D[pixel, cout] = sum over K-segments s, taps, channels of  X_s[pixel + tap, c] * W_s[cout, tap, c]
+ * followed by the fused epilogue  + bias[cout] + temb[b, cout] + residual[pixel, cout].
+ *   segment 0      : the convolution proper (3x3 pad 1, stride 1 or 2; or 1x1)
+ *   segments 1..2  : optional 1x1 "shortcut" convolutions of the block input accumulated into
+ *                    the same output (ResidualBlock.shortcut, dm1:89-92,103; two segments when
+ *                    the block input is the virtual concat [h, skip], dm1:265).
+ * out_mode 0: y NHWC [B,H,W,Cout].
+ * out_mode 1: "qkv split" for AttentionBlock (dm1:114,120-121): cout = head*3*dh + which*dh + d;
+ *             q,k -> [B,heads,T,dh] multiplied by qk_scale (= dh^-1/4), v -> vt [B,heads,dh,T]. */
+typedef struct advs_conv_seg {
+  const void* x; /* NHWC [B, Hin, Win, C]; Hin = H*stride for segment 0, H otherwise */
+  const void* w; /* [Cout][taps][C] in dtype */
+  int32_t C;
+  int32_t taps; /* 9 (3x3 pad 1) or 1 (1x1) */
+} advs_conv_seg;
+
+typedef struct advs_conv_params {
+  int32_t B, H, W; /* output spatial size */
+  int32_t Cout;
+  int32_t stride; /* 1 or 2, segment 0 only */
+  int32_t nseg;
+  advs_conv_seg seg[3];
+  const float* bias;      /* [Cout] or NULL */
+  const float* temb;      /* [B or 1][temb_stride] or NULL: per-image per-channel bias (dm1:101) */
+  int32_t temb_stride;    /* floats between images; 0 = broadcast one row */
+  int32_t out_mode;       /* 0 NHWC, 1 qkv split */
+  const void* residual;   /* NHWC [B,H,W,Cout] or NULL */
+  void* y;                /* out_mode 0 */
+  void* q;                /* out_mode 1 */
+  void* k;
+  void* vt;
+  int32_t heads;
+  float qk_scale;
+  int32_t dtype;
+  int32_t reserved;
+} advs_conv_params;
+
+/* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */
+int advs_conv_simt(const advs_conv_params* p, void* stream);
+
+/* sm_100a tcgen05/TMEM/TMA implementation, bf16 only. C and Cout multiples of 64.
+ * The plan holds the TMA descriptors (they embed the tensor addresses), so it must be
+ * re-created when any pointer in `p` changes.  ADVS_CONV_PLAN_BYTES bytes, 64-byte aligned,
+ * caller-owned host memory. */
+#define ADVS_CONV_PLAN_BYTES 2048
+int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host);
+int advs_conv_sm100_launch(const void* plan_host, void* stream);
+
+/* ---- K7: nearest 2x upsample (dm1:137) ---------------------------------------------------- */
+int advs_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, int dtype,
+                            void* stream);
+
+/* ---- K4: self-attention core softmax(q^T k) v (dm1:122-125) ------------------------------- */
+/* q,k [B,heads,T,dh] (already scaled), vt [B,heads,dh,T], o NHWC [B,T,heads*dh]. */
+size_t advs_attention_simt_workspace_bytes(int B, int heads, int T);
+int advs_attention_simt(const void* q, const void* k, const void* vt, void* o, int B, int heads,
+                        int T, int dh, void* workspace, size_t workspace_bytes, int dtype,
+                        void* stream);
+/* sm_100a flash-attention (tcgen05 QK^T and PV, online softmax in fp32), bf16, dh in {64,128,256},
+ * T multiple of 128. */
+#define ADVS_ATTN_PLAN_BYTES 1024
+int advs_attention_sm100_plan(const void* q, const void* k, const void* vt, void* o, int B,
+                              int heads, int T, int dh, void* plan_host);
+int advs_attention_sm100_launch(const void* plan_host, void* stream);
+
+/* ---- K8: DDIM / DDPM reverse-step updates (dm1:449-472, dm1:356-395) ---------------------- */
+/* coef rows (fp32, device): [sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, pad..]
+ * 8 floats per step.  x' = sqrt(a_prev)*clamp((x - sqrt(1-a_t)*eps)/sqrt(a_t)) + dir*eps + sigma*z
+ * evaluated with exactly the reference's fp32 operation order (no FMA contraction).
+ * step_dev: device int32 holding the row to use (advanced by `advance` after use, so a captured
+ * CUDA graph of one step can be replayed).  noise may be NULL (sigma*z := 0). */
+int advs_ddim_step(const float* x, const float* eps, const float* noise, float* x_out,
+                   size_t n_elems, const float* coef, int32_t* step_dev, int advance,
+                   int clip_denoised, void* stream);
+/* DDPM ancestral step. coef rows: [sqrt_recip_acp, sqrt_recipm1_acp, post_mean_coef1,
+ * post_mean_coef2, exp(0.5*post_log_var)*(t!=0), pad..] 8 floats per step. */
+int advs_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out,
+                   size_t n_elems, const float* coef, int32_t* step_dev, int advance,
+                   int clip_denoised, void* stream);
+/* copy row *step_dev of table[rows][row_floats] to dst (per-step timestep-embedding select) */
+int advs_select_row(const float* table, int row_floats, const int32_t* step_dev, float* dst,
+                    void* stream);
+
+/* ---- K9: shadow mask + compositing (dm2:552-570, dm2:615-654, ts:147-174, ts:224-266) ------ */
+/* mask[b,h,w] = (sqrt((w - cx_b)^2 + (h - cy_b)^2) <= r_b) ? 1 : 0, centers[b] = (c0,c1) used as
+ * (x,y) exactly like dm2:567-569; fp32 arithmetic in the reference's order. */
+int advs_shadow_disk_mask(const float* centers, const float* radii, int B, int H, int W,
+                          float* mask, void* stream);
+/* cv2.GaussianBlur(mask,(5,5),0): separable [1,4,6,4,1]/16, BORDER_REFLECT_101 (ts:147-153) */
+int advs_gaussian_blur5(const float* src, float* dst, int B, int H, int W, void* stream);
+/* combined = shadow_mask * feature_mask (feature_mask [B,Cm,H,W], Cm = 1 or C, broadcast);
+ * shadowed = img*(1-m) + m*(img*(1-intensity))                                   (dm2:642-645)
+ * out      = clamp(img*(1-m) + adv*m, 0, 1), adv = `adv` if given else shadowed   (dm2:650-653)
+ * img/adv/out NCHW fp32 [B,C,H,W].  shadowed_out / out may be NULL to skip that output.
+ * one_minus_intensity = (float)(1.0 - intensity) evaluated by the host in double like Python does. */
+int advs_shadow_composite(const float* img, const float* shadow_mask, const float* feature_mask,
+                          int Cm, const float* adv, float one_minus_intensity, float* shadowed_out,
+                          float* out, int B, int C, int H, int W, void* stream);
+/* fused last step of the shadow sampler: g = clip(x_final, 0, 1) (main.py:135 mapping) is used as
+ * `adv` of advs_shadow_composite; mask is built in-kernel from (centers, radii). */
+int advs_shadow_composite_generated(const float* img, const float* x_final, const float* centers,
+                                    const float* radii, const float* feature_mask, int Cm,
+                                    float* out, int B, int C, int H, int W, void* stream);
+
+/* ---- attack-success decision (ASR_fast.py:101-126) --------------------------------------- */
+/* flags[b] = argmax_c logits[b,c] != labels[b] (first max wins, like torch.max);
+ * counts[0] += number of successes, counts[1] += B. */
+int advs_success_flags(const float* logits, const int64_t* labels, int B, int classes,
+                       uint8_t* flags, int64_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADVSHADOW_B200_H */
