@@ -218,10 +218,12 @@ __global__ void k_ddpm_step(const float* __restrict__ x, const float* __restrict
 __global__ void k_advance_step(int32_t* step_dev, int advance) { *step_dev += advance; }
 
 __global__ void k_select_row(const float* __restrict__ table, int row_floats,
-                             const int32_t* __restrict__ step_dev, float* __restrict__ dst) {
+                             const int32_t* __restrict__ step_dev, float* __restrict__ dst, int reps) {
   const float* src = table + (size_t)(*step_dev) * row_floats;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_floats; i += gridDim.x * blockDim.x)
-    dst[i] = src[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_floats; i += gridDim.x * blockDim.x) {
+    float v = src[i];
+    for (int r = 0; r < reps; ++r) dst[(size_t)r * row_floats + i] = v;
+  }
 }
 
 }  // namespace advs
@@ -339,11 +341,11 @@ int advs_ddpm_step(const float* x, const float* eps, const float* noise, float* 
   return ADVS_OK;
 }
 
-int advs_select_row(const float* table, int row_floats, const int32_t* step_dev, float* dst, void* stream) {
-  ADVS_CHECK_ARG(table && step_dev && dst && row_floats > 0, "select_row: bad args");
+int advs_select_row(const float* table, int row_floats, const int32_t* step_dev, float* dst, int reps, void* stream) {
+  ADVS_CHECK_ARG(table && step_dev && dst && row_floats > 0 && reps > 0, "select_row: bad args");
   int blocks = (row_floats + 255) / 256;
   if (blocks > 148) blocks = 148;
-  k_select_row<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, row_floats, step_dev, dst);
+  k_select_row<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, row_floats, step_dev, dst, reps);
   ADVS_CHECK_LAUNCH("select_row");
   return ADVS_OK;
 }

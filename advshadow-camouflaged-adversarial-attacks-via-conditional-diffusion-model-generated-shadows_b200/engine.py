@@ -1,0 +1,301 @@
+"""Binds a `plan.Plan` to device memory and the C ABI: packs weights, carves the activation arena,
+builds the TMA launch plans and replays the op list on torch's current CUDA stream.
+
+torch is used here for plumbing only (device allocation, streams, parameter storage); every
+arithmetic op on the hot path is one of the library's own kernels.  There is no fallback: a
+non-CUDA device or a missing library raises.
+"""
+import ctypes as C
+import math
+from typing import Dict, List
+
+import torch
+
+from . import _capi as capi
+from .plan import Plan, UNetSpec, build_unet_plan
+
+_DT = {"fp32": capi.F32, "bf16": capi.BF16}
+_TORCH_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class UNetEngine:
+    """One (spec, batch, height, width, precision) instance of the denoiser on one GPU."""
+
+    def __init__(self, spec: UNetSpec, params: Dict[str, torch.Tensor], B: int, H: int, W: int,
+                 precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto"):
+        if precision not in _DT:
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        any_p = next(iter(params.values()))
+        if not any_p.is_cuda:
+            raise RuntimeError("advshadow_b200: the denoiser runs on CUDA only (no CPU path); move the model to a GPU")
+        self.lib = capi.lib()
+        self.device = any_p.device
+        self.spec, self.B, self.H, self.W = spec, B, H, W
+        self.precision = precision
+        self.dt = _DT[precision]
+        self.act_bytes = 2 if precision == "bf16" else 4
+        with torch.cuda.device(self.device):
+            is_sm100 = bool(self.lib.advs_device_is_sm100())
+        if conv_impl == "auto":
+            conv_impl = "sm100" if (precision == "bf16" and is_sm100) else "simt"
+        if attn_impl == "auto":
+            attn_impl = "sm100" if (precision == "bf16" and is_sm100) else "simt"
+        if (conv_impl == "sm100" or attn_impl == "sm100") and precision != "bf16":
+            raise ValueError("the tcgen05 kernels are bf16-only; use precision='bf16'")
+        self.conv_impl, self.attn_impl = conv_impl, attn_impl
+
+        plan = build_unet_plan(spec, B, H, W, attn_scores_ws=False)
+        if any(not self._attn_sm100_ok(op.args) for op in plan.ops if op.kind == "attn"):
+            plan = build_unet_plan(spec, B, H, W, attn_scores_ws=True)
+        self.plan: Plan = plan
+        for b in plan.bufs.values():
+            if b.shape and b.shape[0] == "gn_ws":
+                _, bb, hw, c = b.shape
+                b.elems = int(self.lib.advs_groupnorm_workspace_bytes(bb, hw, c)) // 4
+        plan.assign_offsets(self.act_bytes)
+
+        dev = self.device
+        self.arena = torch.empty(max(plan.arena_bytes, 1024), dtype=torch.uint8, device=dev)
+        self.x = torch.zeros(B, spec.in_channels, H, W, dtype=torch.float32, device=dev)
+        self.eps = torch.zeros(B, spec.out_channels, H, W, dtype=torch.float32, device=dev)
+        self.temb_cur = torch.zeros(B, plan.temb_total, dtype=torch.float32, device=dev)
+        half = spec.model_channels // 2
+        # the reference evaluates this table on the host in fp32 (dm1:25-28) and uploads it
+        self.freqs = torch.exp(-math.log(10000) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(dev)
+        self._keep: List[object] = []     # packed weights, biases, plan blobs
+        self._launches = []
+        self._weights_loaded = False
+        self._packed: Dict[tuple, torch.Tensor] = {}
+        self._bias: Dict[tuple, torch.Tensor] = {}
+        self._build_static()
+        self.load_weights(params)
+        self._build_launches()
+
+    # ---- helpers ----
+    def _attn_sm100_ok(self, a):
+        return self.attn_impl == "sm100" and a["T"] % 128 == 0 and a["dh"] in (64, 128, 256)
+
+    def _conv_sm100_ok(self, a):
+        if self.conv_impl != "sm100":
+            return False
+        if a["cout"] % 64:
+            return False
+        for (src, _, _, _) in a["segs"]:
+            if self.plan.shape(src)[3] % 64:
+                return False
+        if a["qkv"] is not None and (a["cout"] // (3 * a["heads"])) % 32:
+            return False
+        return True
+
+    def _ptr(self, buf):
+        return self.arena.data_ptr() + self.plan.bufs[buf].offset
+
+    def buffer_view(self, buf):
+        """torch view of an arena buffer (debug / tests)."""
+        b = self.plan.bufs[buf]
+        dt = _TORCH_DT[self.precision] if b.kind == "act" else torch.float32
+        n = b.elems * (self.act_bytes if b.kind == "act" else 4)
+        return self.arena[b.offset:b.offset + n].view(dt).view(*[s for s in b.shape if not isinstance(s, str)])
+
+    # ---- static allocations that depend only on shapes ----
+    def _build_static(self):
+        dev, tdt = self.device, _TORCH_DT[self.precision]
+        spec = self.spec
+        for op in self.plan.ops:
+            a = op.args
+            if op.kind in ("stem", "head"):
+                self._packed[(a["weight"], None)] = torch.empty(a["cout"], 9, a["cin"], dtype=torch.float32, device=dev)
+                self._bias[(a["weight"],)] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
+            elif op.kind == "conv":
+                for (src, wname, taps, sl) in a["segs"]:
+                    c = self.plan.shape(src)[3]
+                    self._packed[(wname, sl)] = torch.empty(a["cout"], taps, c, dtype=tdt, device=dev)
+                if a["bias"]:
+                    self._bias[tuple(a["bias"])] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
+        ted = spec.time_embed_dim
+        self.temb_w = torch.empty(self.plan.temb_total, ted, dtype=torch.float32, device=dev)
+        self.temb_b = torch.empty(self.plan.temb_total, dtype=torch.float32, device=dev)
+
+    # ---- weights ----
+    def load_weights(self, params: Dict[str, torch.Tensor]):
+        """(Re)pack every parameter into the kernels' layouts.  Pointers stay fixed, so launch plans
+        and captured CUDA graphs remain valid after a reload."""
+        st = _stream_ptr()
+        self._params = {k: v.detach() for k, v in params.items()}
+
+        def p32(name):
+            t = self._params[name]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+                self._keep.append(t)
+            return t
+
+        with torch.cuda.device(self.device):
+            for (wname, sl), dst in self._packed.items():
+                w = p32(wname + ".weight")
+                if sl is not None:
+                    w = w[:, sl[0]:sl[1]].contiguous()
+                O, I, kh, kw = w.shape
+                dt = capi.F32 if dst.dtype == torch.float32 else capi.BF16
+                capi.call("advs_pack_conv_weight", w.data_ptr(), dst.data_ptr(), O, I, kh, kw, dt, st)
+                self._keep.append(w)
+            for names, dst in self._bias.items():
+                acc = p32(names[0] + ".bias").clone()
+                for n in names[1:]:
+                    acc += p32(n + ".bias")
+                dst.copy_(acc)
+            off = 0
+            for slot in self.plan.temb_slots:
+                self.temb_w[off:off + slot.cout].copy_(p32(slot.weight + ".weight"))
+                self.temb_b[off:off + slot.cout].copy_(p32(slot.weight + ".bias"))
+                off += slot.cout
+            self.te0_w, self.te0_b = p32("time_embed.0.weight"), p32("time_embed.0.bias")
+            self.te2_w, self.te2_b = p32("time_embed.2.weight"), p32("time_embed.2.bias")
+            self._gn = {}
+            for op in self.plan.ops:
+                if op.kind == "gn":
+                    n = op.args["weight"]
+                    self._gn[n] = (p32(n + ".weight"), p32(n + ".bias"))
+        if self._weights_loaded:
+            # GroupNorm affine pointers are baked into the launch list
+            self._build_launches()
+        self._weights_loaded = True
+
+    # ---- launch list ----
+    def _build_launches(self):
+        L = []
+        lib, plan, dt = self.lib, self.plan, self.dt
+        B = self.B
+        self._plans = []
+        self.n_kernels = 0
+        for op in plan.ops:
+            a = op.args
+            if op.kind == "stem":
+                w, b = self._packed[(a["weight"], None)], self._bias[(a["weight"],)]
+                L.append((lib.advs_conv3x3_stem, (self.x.data_ptr(), w.data_ptr(), b.data_ptr(), self._ptr(a["dst"]),
+                                                  B, a["H"], a["W"], a["cin"], a["cout"], dt), "stem"))
+                self.n_kernels += 1
+            elif op.kind == "head":
+                w, b = self._packed[(a["weight"], None)], self._bias[(a["weight"],)]
+                L.append((lib.advs_conv3x3_head, (self._ptr(a["src"]), w.data_ptr(), b.data_ptr(), self.eps.data_ptr(),
+                                                  B, a["H"], a["W"], a["cin"], a["cout"], dt), "head"))
+                self.n_kernels += 1
+            elif op.kind == "gn":
+                srcs = a["srcs"]
+                x0, c0 = self._ptr(srcs[0]), plan.shape(srcs[0])[3]
+                x1, c1 = (self._ptr(srcs[1]), plan.shape(srcs[1])[3]) if len(srcs) > 1 else (None, 0)
+                g, bt = self._gn[a["weight"]]
+                wsb = plan.bufs[a["ws"]]
+                L.append((lib.advs_groupnorm_stats, (x0, c0, x1, c1, B, a["HW"], a["groups"], 1e-5, g.data_ptr(),
+                                                     bt.data_ptr(), self._ptr(a["ss"]), self._ptr(a["ws"]),
+                                                     wsb.elems * 4, dt), "gn_stats"))
+                L.append((lib.advs_groupnorm_apply, (x0, c0, x1, c1, B, a["HW"], self._ptr(a["ss"]),
+                                                     1 if a["silu"] else 0, self._ptr(a["dst"]), dt), "gn_apply"))
+                self.n_kernels += 3 + (1 if len(srcs) > 1 else 0)
+            elif op.kind == "conv":
+                cp = capi.ConvParams()
+                cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], a["cout"], a["stride"], len(a["segs"])
+                for i, (src, wname, taps, sl) in enumerate(a["segs"]):
+                    cp.seg[i].x = self._ptr(src)
+                    cp.seg[i].w = self._packed[(wname, sl)].data_ptr()
+                    cp.seg[i].C = plan.shape(src)[3]
+                    cp.seg[i].taps = taps
+                cp.bias = self._bias[tuple(a["bias"])].data_ptr() if a["bias"] else None
+                if a["temb"] is not None:
+                    cp.temb = self.temb_cur.data_ptr() + 4 * a["temb"]
+                    cp.temb_stride = plan.temb_total
+                cp.residual = self._ptr(a["residual"]) if a["residual"] else None
+                if a["qkv"] is not None:
+                    cp.out_mode = 1
+                    cp.q, cp.k, cp.vt = (self._ptr(x) for x in a["qkv"])
+                    cp.heads = a["heads"]
+                    cp.qk_scale = 1.0 / math.sqrt(math.sqrt(a["cout"] // (3 * a["heads"])))
+                else:
+                    cp.out_mode = 0
+                    cp.y = self._ptr(a["dst"])
+                cp.dtype = dt
+                self._keep.append(cp)
+                if self._conv_sm100_ok(a):
+                    pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+                    with torch.cuda.device(self.device):
+                        capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+                    self._plans.append(pb)
+                    L.append((lib.advs_conv_sm100_launch, (pb.ptr,), "conv_sm100"))
+                else:
+                    L.append((lib.advs_conv_simt, (C.byref(cp),), "conv_simt"))
+                self.n_kernels += 1
+            elif op.kind == "attn":
+                if self._attn_sm100_ok(a):
+                    pb = capi.PlanBuffer(capi.ATTN_PLAN_BYTES)
+                    with torch.cuda.device(self.device):
+                        capi.call("advs_attention_sm100_plan", self._ptr(a["q"]), self._ptr(a["k"]), self._ptr(a["vt"]),
+                                  self._ptr(a["dst"]), B, a["heads"], a["T"], a["dh"], pb.ptr)
+                    self._plans.append(pb)
+                    L.append((lib.advs_attention_sm100_launch, (pb.ptr,), "attn_sm100"))
+                    self.n_kernels += 1
+                else:
+                    wsb = plan.bufs[a["ws"]]
+                    L.append((lib.advs_attention_simt, (self._ptr(a["q"]), self._ptr(a["k"]), self._ptr(a["vt"]),
+                                                        self._ptr(a["dst"]), B, a["heads"], a["T"], a["dh"],
+                                                        self._ptr(a["ws"]), wsb.elems * 4, dt), "attn_simt"))
+                    self.n_kernels += 3
+            elif op.kind == "up":
+                L.append((lib.advs_upsample_nearest2x, (self._ptr(a["src"]), self._ptr(a["dst"]), B, a["H"], a["W"],
+                                                        a["C"], dt), "upsample"))
+                self.n_kernels += 1
+            else:
+                raise AssertionError(op.kind)
+        self._launches = L
+
+    # ---- execution ----
+    def run(self):
+        """eps = UNet(self.x; self.temb_cur) -- enqueue the whole forward on the current stream."""
+        st = _stream_ptr()
+        last_error = self.lib.advs_last_error
+        for fn, args, name in self._launches:
+            rc = fn(*args, st)
+            if rc:
+                raise capi.AdvsError(f"{name} failed (rc={rc}): {last_error().decode()}")
+
+    def temb_table(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """[Nt] int64 timesteps -> [Nt, temb_total] stacked per-block projections
+        Linear(SiLU(time_embed(timestep_embedding(t))))  (dm1:254, dm1:77-80,101)."""
+        t = timesteps.to(device=self.device, dtype=torch.int64).contiguous()
+        nt = t.numel()
+        mc, ted = self.spec.model_channels, self.spec.time_embed_dim
+        dev = self.device
+        e0 = torch.empty(nt, mc, dtype=torch.float32, device=dev)
+        if mc % 2:
+            raise ValueError("model_channels must be even")
+        e1 = torch.empty(nt, ted, dtype=torch.float32, device=dev)
+        e2 = torch.empty(nt, ted, dtype=torch.float32, device=dev)
+        out = torch.empty(nt, self.plan.temb_total, dtype=torch.float32, device=dev)
+        st = _stream_ptr()
+        with torch.cuda.device(dev):
+            capi.call("advs_timestep_embedding", t.data_ptr(), nt, self.freqs.data_ptr(), mc // 2, e0.data_ptr(), st)
+            capi.call("advs_linear_f32", e0.data_ptr(), self.te0_w.data_ptr(), self.te0_b.data_ptr(), e1.data_ptr(),
+                      nt, mc, ted, 0, 1, st)
+            capi.call("advs_linear_f32", e1.data_ptr(), self.te2_w.data_ptr(), self.te2_b.data_ptr(), e2.data_ptr(),
+                      nt, ted, ted, 0, 0, st)
+            capi.call("advs_linear_f32", e2.data_ptr(), self.temb_w.data_ptr(), self.temb_b.data_ptr(), out.data_ptr(),
+                      nt, ted, self.plan.temb_total, 1, 0, st)
+        self._last_emb = e2
+        return out
+
+    def forward(self, x: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
+        if tuple(x.shape) != tuple(self.x.shape):
+            raise ValueError(f"engine built for input {tuple(self.x.shape)}, got {tuple(x.shape)}")
+        with torch.cuda.device(self.device):
+            self.x.copy_(x)
+            table = self.temb_table(timesteps.reshape(-1))
+            if table.shape[0] == 1 and self.B > 1:
+                table = table.expand(self.B, -1)
+            if table.shape[0] != self.B:
+                raise ValueError("timesteps must have one entry per batch element")
+            self.temb_cur.copy_(table)
+            self.run()
+            return self.eps.clone()

@@ -163,9 +163,10 @@ int advs_ddim_step(const float* x, const float* eps, const float* noise, float* 
 int advs_ddpm_step(const float* x, const float* eps, const float* noise, float* x_out,
                    size_t n_elems, const float* coef, int32_t* step_dev, int advance,
                    int clip_denoised, void* stream);
-/* copy row *step_dev of table[rows][row_floats] to dst (per-step timestep-embedding select) */
+/* copy row *step_dev of table[rows][row_floats] to each of the `reps` rows of dst[reps][row_floats]
+ * (per-step timestep-embedding select: ddim_sample feeds the same t to every image, dm1:446) */
 int advs_select_row(const float* table, int row_floats, const int32_t* step_dev, float* dst,
-                    void* stream);
+                    int reps, void* stream);
 
 /* ---- K9: shadow mask + compositing (dm2:552-570, dm2:615-654, ts:147-174, ts:224-266) ------ */
 /* mask[b,h,w] = (sqrt((w - cx_b)^2 + (h - cy_b)^2) <= r_b) ? 1 : 0, centers[b] = (c0,c1) used as

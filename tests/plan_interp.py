@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE: replays a `plan.Plan` with plain PyTorch ops on the CPU.
+
+Purpose: prove on a GPU-less box that the op list / buffer wiring / fused-epilogue bookkeeping the
+CUDA engine executes is the reference's UNet (diff_model.py:245-267).  `round_bf16=True` rounds every
+activation buffer to bf16 at the points the bf16 engine does, which gives a CPU estimate of the
+bf16-mode error.  Never imported by the product.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def temb_table(plan, params, timesteps):
+    mc = plan.spec.model_channels
+    half = mc // 2
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    e = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    e = F.linear(e, params["time_embed.0.weight"], params["time_embed.0.bias"])
+    e = F.linear(F.silu(e), params["time_embed.2.weight"], params["time_embed.2.bias"])
+    cols = [F.linear(F.silu(e), params[s.weight + ".weight"], params[s.weight + ".bias"]) for s in plan.temb_slots]
+    return torch.cat(cols, 1)
+
+
+def run_plan(plan, params, x, timesteps, round_bf16=False):
+    rnd = (lambda t: t.to(torch.bfloat16).float()) if round_bf16 else (lambda t: t)
+    wr = (lambda t: t.to(torch.bfloat16).float()) if round_bf16 else (lambda t: t)   # weight rounding
+    table = temb_table(plan, params, timesteps)
+    if table.shape[0] == 1:
+        table = table.expand(x.shape[0], -1)
+    bufs = {}
+    eps = None
+    for op in plan.ops:
+        a = op.args
+        if op.kind == "stem":
+            y = F.conv2d(x, params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
+            bufs[a["dst"]] = rnd(_nhwc(y))
+        elif op.kind == "gn":
+            xin = torch.cat([bufs[s] for s in a["srcs"]], 3)
+            y = F.group_norm(_nchw(xin), a["groups"], params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], 1e-5)
+            if a["silu"]:
+                y = F.silu(y)
+            bufs[a["dst"]] = rnd(_nhwc(y))
+        elif op.kind == "conv":
+            acc = None
+            for i, (src, wname, taps, sl) in enumerate(a["segs"]):
+                w = params[wname + ".weight"]
+                if sl is not None:
+                    w = w[:, sl[0]:sl[1]]
+                xi = _nchw(bufs[src])
+                if taps == 9:
+                    y = F.conv2d(xi, wr(w), None, stride=a["stride"] if i == 0 else 1, padding=1)
+                else:
+                    y = F.conv2d(xi, wr(w), None)
+                acc = y if acc is None else acc + y
+            for bn in a["bias"]:
+                acc = acc + params[bn + ".bias"][None, :, None, None]
+            if a["temb"] is not None:
+                acc = acc + table[:, a["temb"]:a["temb"] + a["cout"]][:, :, None, None]
+            if a["residual"]:
+                acc = acc + _nchw(bufs[a["residual"]])
+            if a["qkv"] is not None:
+                B, C3, H, W = acc.shape
+                heads = a["heads"]
+                dh = C3 // (3 * heads)
+                scale = 1.0 / math.sqrt(math.sqrt(dh))
+                qkv = acc.reshape(B, heads, 3, dh, H * W)
+                bufs[a["qkv"][0]] = rnd((qkv[:, :, 0] * scale).transpose(2, 3).contiguous())   # [B,h,T,dh]
+                bufs[a["qkv"][1]] = rnd((qkv[:, :, 1] * scale).transpose(2, 3).contiguous())
+                bufs[a["qkv"][2]] = rnd(qkv[:, :, 2].contiguous())                              # [B,h,dh,T]
+            else:
+                bufs[a["dst"]] = rnd(_nhwc(acc))
+        elif op.kind == "attn":
+            q, k, vt = bufs[a["q"]], bufs[a["k"]], bufs[a["vt"]]
+            s = torch.einsum("bhtd,bhsd->bhts", q, k).softmax(-1)
+            o = torch.einsum("bhts,bhds->bthd", s, vt)                                          # [B,T,h,dh]
+            B, T = o.shape[0], o.shape[1]
+            H, W = plan.bufs[a["dst"]].shape[1:3]
+            bufs[a["dst"]] = rnd(o.reshape(B, H, W, -1))
+        elif op.kind == "up":
+            y = F.interpolate(_nchw(bufs[a["src"]]), scale_factor=2, mode="nearest")
+            bufs[a["dst"]] = _nhwc(y)
+        elif op.kind == "head":
+            eps = F.conv2d(_nchw(bufs[a["src"]]), params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
+        else:
+            raise AssertionError(op.kind)
+    return eps

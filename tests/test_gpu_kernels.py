@@ -1,0 +1,179 @@
+"""Per-kernel numerics on the B200, through the C ABI (ops.py -> ctypes -> libadvshadow_b200.so).
+Each kernel is compared with a plain PyTorch fp32 evaluation of the same reference op
+(nn.Conv2d / GroupNorm / softmax-einsum: dm1:62-127) on the same inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import advshadow_b200
+    from advshadow_b200 import ops as o
+    assert torch.cuda.is_available()
+    return o
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+@pytest.mark.parametrize("c0,c1,silu", [(128, 0, True), (256, 128, True), (384, 0, False), (1024, 512, True)])
+def test_groupnorm(ops, dtype, tol, c0, c1, silu):
+    torch.manual_seed(0)
+    B, H, W = 3, 16, 24
+    x0 = (torch.randn(B, H, W, c0, device="cuda") * 2 + 0.5).to(dtype)
+    x1 = (torch.randn(B, H, W, c1, device="cuda") - 1).to(dtype) if c1 else None
+    g = torch.randn(c0 + c1, device="cuda")
+    b = torch.randn(c0 + c1, device="cuda")
+    y = ops.groupnorm(x0, x1, g, b, silu=silu)
+    xin = torch.cat([x0, x1], 3) if c1 else x0
+    ref = F.group_norm(nchw(xin.float()), 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert rel_err(nchw(y), ref) < tol
+
+
+CONV_CASES = [
+    # B, H, W, cin, cout, taps, stride
+    (2, 16, 16, 128, 128, 9, 1),
+    (1, 32, 32, 64, 256, 9, 1),
+    (3, 8, 8, 256, 128, 9, 1),      # tile spans images (tn > 1)
+    (2, 16, 16, 128, 192, 1, 1),    # 1x1, Cout not a multiple of 128
+    (2, 16, 16, 128, 128, 9, 2),    # stride 2 (output 16x16 from 32x32)
+    (1, 28, 28, 64, 64, 9, 1),      # non power-of-two width (224/8)
+    (1, 4, 256, 64, 128, 9, 1),     # W > 128: row segments
+]
+
+
+def conv_ref(x_nhwc, w, stride, bias=None):
+    pad = 1 if w.shape[-1] == 3 else 0
+    return F.conv2d(nchw(x_nhwc.float()), w.float(), bias, stride=stride, padding=pad)
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 2e-5), ("simt", torch.bfloat16, 1e-2),
+                                            ("sm100", torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_plain(ops, impl, dtype, tol, case):
+    B, H, W, cin, cout, taps, stride = case
+    k = 3 if taps == 9 else 1
+    torch.manual_seed(1)
+    x = torch.randn(B, H * stride, W * stride, cin, device="cuda").to(dtype)
+    w = (torch.randn(cout, cin, k, k, device="cuda") / math.sqrt(cin * taps)).to(dtype).float()
+    bias = torch.randn(cout, device="cuda")
+    wp = ops.pack_conv_weight(w, dtype)
+    y = ops.conv([(x, wp)], B, H, W, cout, stride=stride, bias=bias, impl=impl)
+    torch.cuda.synchronize()
+    ref = conv_ref(x, w, stride, bias)
+    assert rel_err(nchw(y), ref) < tol
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 2e-5), ("sm100", torch.bfloat16, 1e-2)])
+def test_conv_fused_resblock_tail(ops, impl, dtype, tol):
+    """conv2 of a ResidualBlock whose input is a virtual concat: 3x3 conv + two 1x1 shortcut
+    K-segments + bias, and conv1 with the per-image time-embedding bias (dm1:94-103)."""
+    torch.manual_seed(2)
+    B, H, W, c0, c1, cout = 2, 16, 16, 128, 64, 128
+    h = torch.randn(B, H, W, cout, device="cuda").to(dtype)
+    xa = torch.randn(B, H, W, c0, device="cuda").to(dtype)
+    xb = torch.randn(B, H, W, c1, device="cuda").to(dtype)
+    w2 = (torch.randn(cout, cout, 3, 3, device="cuda") / 34).to(dtype).float()
+    ws = (torch.randn(cout, c0 + c1, 1, 1, device="cuda") / 14).to(dtype).float()
+    bias = torch.randn(cout, device="cuda")
+    segs = [(h, ops.pack_conv_weight(w2, dtype)), (xa, ops.pack_conv_weight(ws[:, :c0].contiguous(), dtype)),
+            (xb, ops.pack_conv_weight(ws[:, c0:].contiguous(), dtype))]
+    y = ops.conv(segs, B, H, W, cout, bias=bias, impl=impl)
+    ref = conv_ref(h, w2, 1) + conv_ref(torch.cat([xa, xb], 3), ws, 1) + bias[None, :, None, None]
+    assert rel_err(nchw(y), ref) < tol
+    # conv1: + temb[b, :] ; identity residual
+    temb = torch.randn(B, 512, device="cuda")
+    y = ops.conv([(h, segs[0][1])], B, H, W, cout, bias=bias, temb=temb[:, 128:256].contiguous(), residual=xa, impl=impl)
+    ref = conv_ref(h, w2, 1, bias) + temb[:, 128:256, None, None] + nchw(xa.float())
+    assert rel_err(nchw(y), ref) < tol
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 2e-5), ("sm100", torch.bfloat16, 1e-2)])
+def test_conv_qkv_split(ops, impl, dtype, tol):
+    torch.manual_seed(3)
+    B, H, W, c, heads = 2, 16, 8, 256, 4
+    dh = c // heads
+    x = torch.randn(B, H, W, c, device="cuda").to(dtype)
+    w = (torch.randn(3 * c, c, 1, 1, device="cuda") / 16).to(dtype).float()
+    q, k, vt = ops.conv([(x, ops.pack_conv_weight(w, dtype))], B, H, W, 3 * c, qkv_heads=heads, impl=impl)
+    ref = conv_ref(x, w, 1).reshape(B, heads, 3, dh, H * W)       # dm1:119-120 per-head [q|k|v] interleave
+    s = 1 / math.sqrt(math.sqrt(dh))
+    assert rel_err(q, (ref[:, :, 0] * s).transpose(2, 3)) < tol
+    assert rel_err(k, (ref[:, :, 1] * s).transpose(2, 3)) < tol
+    assert rel_err(vt, ref[:, :, 2]) < tol
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 2e-5), ("simt", torch.bfloat16, 1e-2),
+                                            ("sm100", torch.bfloat16, 1.5e-2)])
+@pytest.mark.parametrize("T,dh", [(128, 64), (256, 128), (512, 256), (1024, 128)])
+def test_attention(ops, impl, dtype, tol, T, dh):
+    torch.manual_seed(4)
+    B, heads = 2, 2
+    q = (torch.randn(B, heads, T, dh, device="cuda") * 0.7).to(dtype)
+    k = (torch.randn(B, heads, T, dh, device="cuda") * 0.7).to(dtype)
+    vt = torch.randn(B, heads, dh, T, device="cuda").to(dtype)
+    o = ops.attention(q, k, vt, impl=impl)
+    torch.cuda.synchronize()
+    p = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()).softmax(-1)
+    ref = torch.einsum("bhts,bhds->bthd", p, vt.float()).reshape(B, T, heads * dh)
+    assert rel_err(o, ref) < tol
+
+
+def test_attention_lazy_rescale_path(ops):
+    """keys whose scores grow block after block force the running-max rescale of the O accumulator."""
+    torch.manual_seed(5)
+    B, heads, T, dh = 1, 1, 1024, 128
+    q = torch.ones(B, heads, T, dh, device="cuda").to(torch.bfloat16) * 0.25
+    ramp = torch.linspace(0, 3.0, T, device="cuda")[None, None, :, None]
+    k = (torch.ones(B, heads, T, dh, device="cuda") * ramp * 0.25).to(torch.bfloat16)
+    vt = torch.randn(B, heads, dh, T, device="cuda").to(torch.bfloat16)
+    o = ops.attention(q, k, vt, impl="sm100")
+    p = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()).softmax(-1)
+    ref = torch.einsum("bhts,bhds->bthd", p, vt.float()).reshape(B, T, heads * dh)
+    assert rel_err(o, ref) < 2e-2
+
+
+def test_upsample_and_edges(ops):
+    torch.manual_seed(6)
+    x = torch.randn(2, 5, 7, 64, device="cuda").to(torch.bfloat16)
+    y = ops.upsample_nearest2x(x)
+    ref = F.interpolate(nchw(x.float()), scale_factor=2, mode="nearest")
+    assert torch.equal(nchw(y.float()), ref)
+
+
+def test_timestep_embedding(ops):
+    t = torch.tensor([0, 1, 17, 501, 981, 999], device="cuda")
+    e = ops.timestep_embedding(t, 128)
+    half = 64
+    freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = t.cpu()[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (e.cpu() - ref).abs().max().item() < 2e-6
+
+
+def test_success_flags(ops):
+    torch.manual_seed(7)
+    logits = torch.randn(300, 37, device="cuda")
+    labels = torch.randint(0, 37, (300,), device="cuda")
+    labels[:100] = logits[:100].argmax(1)
+    flags, counts = ops.success_flags(logits, labels)
+    ref = (logits.argmax(1) != labels)
+    assert torch.equal(flags.bool(), ref)
+    assert counts.tolist() == [int(ref.sum()), 300]
