@@ -15,6 +15,9 @@ def ops():
     import advshadow_b200
     from advshadow_b200 import ops as o
     assert torch.cuda.is_available()
+    # the PyTorch side is the fp32 reference: keep cuDNN / cuBLAS from silently using TF32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return o
 
 

@@ -1,0 +1,198 @@
+"""CPU tests (-m "not gpu"): pin the oracle port against the golden vectors minted from the unmodified
+reference, check the host logic (schedules, DDIM tables, plan wiring, state_dict surface, errors) and
+that the C-ABI library loads and exports every declared symbol.  No GPU compute here."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_port as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def seeded_params(flavour):
+    import advshadow_b200
+    from advshadow_b200 import diff_model, diff_model2
+    torch.manual_seed(0)
+    if flavour == "dm1":
+        m = diff_model.UNetModel()
+    elif flavour == "main":
+        m = diff_model.UNetModel(channel_mult=(1, 2, 2, 2), attention_resolutions=(2,), dropout=0.1)
+    else:
+        m = diff_model2.UNetModel()
+    return m, {k: v.detach() for k, v in m.state_dict().items()}
+
+
+@pytest.fixture(scope="module")
+def dm1_params():
+    return seeded_params("dm1")
+
+
+def test_port_unet_forward_matches_reference_golden(golden, dm1_params):
+    g = golden("forwards.pt")
+    m, p = dm1_params
+    chk = float(sum(v.detach().double().abs().sum() for v in m.parameters()))
+    assert abs(chk - g["dm1_checksum"]) <= 1e-9 * chk
+    with torch.no_grad():
+        for key in ("dm1_32", "dm1_64"):
+            c = g[key]
+            e = P.unet_forward(p, P.DM1_CFG, c["x"], c["t"])
+            assert (e - c["eps"]).abs().max().item() < 2e-5
+    m3, p3 = seeded_params("main")
+    c = g["main_32"]
+    with torch.no_grad():
+        e = P.unet_forward(p3, dict(P.DM1_CFG, attention_resolutions=(2,)), c["x"], c["t"])
+    assert (e - c["eps"]).abs().max().item() < 2e-5
+
+
+def test_port_dm2_forward_matches_reference_golden(golden):
+    g = golden("forwards.pt")
+    m, p = seeded_params("dm2")
+    chk = float(sum(v.detach().double().abs().sum() for v in m.parameters()))
+    assert abs(chk - g["dm2_checksum"]) <= 1e-9 * chk
+    c = g["dm2_64"]
+    with torch.no_grad():
+        e = P.unet_forward(p, P.DM2_CFG, c["x"], c["t"])
+    assert (e - c["eps"]).abs().max().item() < 2e-5
+
+
+def test_port_ddim_config1_matches_reference_golden(golden, dm1_params):
+    g = golden("config1.pt")
+    _, p = dm1_params
+    acp = P.cosine_alphas_cumprod()
+    # teacher-forced updates are bit-exact, the 10-step free run stays within fp32 reorder noise
+    n = g["trace_x"].shape[0]
+    seq = np.asarray(list(range(0, 1000, 100))) + 1
+    prev = np.append(np.array([0]), seq[:-1])
+    for j, i in enumerate(reversed(range(n))):
+        a_t = acp[int(seq[i])].float().reshape(1, 1, 1, 1)
+        a_p = acp[int(prev[i])].float().reshape(1, 1, 1, 1)
+        nxt = g["trace_x"][j + 1] if j + 1 < n else g["final"]
+        assert torch.equal(P.ddim_update(g["trace_x"][j], g["trace_eps"][j], a_t, a_p), nxt)
+    x = P.ddim_sample(p, P.DM1_CFG, acp, g["x_T"], 10)
+    assert (x - g["final"]).abs().max().item() < 1e-4
+
+
+def test_port_shadow_matches_reference_golden(golden):
+    for c in golden("shadow.pt"):
+        H, W = c["img"].shape[1:]
+        assert torch.equal(P.create_shadow_mask(H, W, c["center"], c["radius"]), c["mask"])
+        out, shadowed, _ = P.apply_shadow(c["img"], c["center"], c["radius"], c["fm"], c["intensity"],
+                                          perturb=lambda s: c["adv"])
+        assert torch.equal(shadowed, c["shadowed"])
+        assert torch.equal(out, c["out"])
+    g = golden("config1.pt")
+    gen01 = g["final"].clamp(0, 1)
+    out, shadowed, _ = P.apply_shadow(g["clean"], g["center"], g["radius"], g["feature_mask"], 0.33,
+                                      perturb=lambda s: gen01)
+    assert torch.equal(out, g["composite"]) and torch.equal(shadowed, g["shadowed"])
+
+
+def test_port_blur_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    torch.manual_seed(0)
+    m = (torch.rand(41, 29) > 0.5).float()
+    assert np.array_equal(P.gaussian_blur5(m).numpy(), cv2.GaussianBlur(m.numpy(), (5, 5), 0))
+    imp = torch.zeros(9, 9)
+    imp[0, 0] = 1
+    assert np.array_equal(P.gaussian_blur5(imp).numpy(), cv2.GaussianBlur(imp.numpy(), (5, 5), 0))
+
+
+def test_schedules_match_reference_golden(golden):
+    import advshadow_b200
+    from advshadow_b200 import diff_model, diff_model2
+    g = golden("schedules.pt")
+    for name, gd in (("cosine", diff_model.GaussianDiffusion()), ("linear", diff_model2.GaussianDiffusion())):
+        for k, v in g[name].items():
+            assert torch.equal(getattr(gd, k), v), (name, k)
+    assert torch.equal(P.cosine_alphas_cumprod(), g["cosine"]["alphas_cumprod"])
+    assert torch.equal(P.linear_alphas_cumprod(), g["linear"]["alphas_cumprod"])
+    with pytest.raises(ValueError):
+        diff_model.GaussianDiffusion(beta_schedule="sigmoid")
+
+
+def test_ddim_tables_and_quirks():
+    import advshadow_b200
+    from advshadow_b200.diff_model import GaussianDiffusion, ddim_timestep_tables
+    seq, prev = ddim_timestep_tables(1000, 10, "uniform")
+    assert list(seq) == [1, 101, 201, 301, 401, 501, 601, 701, 801, 901] and list(prev) == [0] + list(seq[:-1])
+    seq, _ = ddim_timestep_tables(1000, 30, "uniform")        # T % n != 0: over-long table (dm1:429-430)
+    assert len(seq) == 31 and seq[29] == 958
+    seq, _ = ddim_timestep_tables(1000, 20, "quad")
+    assert seq[0] == 1 and seq[-1] == 800 + 1   # int(sqrt(800)**2) + 1
+    with pytest.raises(NotImplementedError):
+        ddim_timestep_tables(1000, 10, "cubic")
+    gd = GaussianDiffusion()
+    seq, prev = ddim_timestep_tables(1000, 10, "uniform")
+    coef = gd.ddim_coefficients(seq, prev, 10, 0.0)
+    assert coef.shape == (10, 8) and coef.dtype == torch.float32
+    a_t = gd.alphas_cumprod[901].float()
+    assert coef[0, 0] == torch.sqrt(1. - a_t) and coef[0, 1] == torch.sqrt(a_t)
+    assert coef[9, 2] == torch.sqrt(gd.alphas_cumprod[0].float())   # last step uses a[0], not 1 (dm1:440)
+    assert float(coef[:, 4].abs().max()) == 0.0
+    assert gd.ddpm_coefficients().shape == (1000, 8) and float(gd.ddpm_coefficients()[-1, 4]) == 0.0
+
+
+def test_plan_wiring_equals_port(dm1_params):
+    """The op list the CUDA engine executes, replayed with torch ops, equals the oracle port."""
+    import advshadow_b200
+    from advshadow_b200.plan import UNetSpec, build_unet_plan, parameter_shapes
+    import plan_interp
+    m, p = dm1_params
+    assert list(parameter_shapes(UNetSpec()).items()) == [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    torch.manual_seed(5)
+    x, t = torch.randn(2, 3, 32, 32), torch.tensor([7, 640])
+    plan = build_unet_plan(UNetSpec(), 2, 32, 32)
+    with torch.no_grad():
+        assert (plan_interp.run_plan(plan, p, x, t) - P.unet_forward(p, P.DM1_CFG, x, t)).abs().max().item() < 2e-5
+    plan.assign_offsets(2)
+    live = sorted((b.first, b.last, b.offset, b.nbytes) for b in plan.bufs.values() if b.nbytes)
+    for i, a in enumerate(live):            # no two simultaneously-live buffers may overlap in the arena
+        for b in live[i + 1:]:
+            if b[0] <= a[1] and a[0] <= b[1]:
+                assert a[2] + a[3] <= b[2] or b[2] + b[3] <= a[2]
+    assert abs(build_unet_plan(UNetSpec(), 1, 64, 64).flops / 1e9 - 45.9) < 0.1
+    dm2 = UNetSpec(num_res_blocks=3, attention_resolutions=(4, 8, 16, 32), channel_mult=(1, 2, 4, 8))
+    assert abs(build_unet_plan(dm2, 1, 256, 256).flops / 1e9 - 2195.1) < 0.1
+    with pytest.raises(ValueError):
+        build_unet_plan(UNetSpec(), 1, 36, 36)
+
+
+def test_capi_library_exports_every_declared_symbol():
+    import advshadow_b200
+    from advshadow_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "advshadow_b200.h")).read()
+    declared = set(re.findall(r"\b(advs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_capi.SIGNATURES)
+    lib = _capi.lib()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.advs_version() >= 100
+    import ctypes
+    assert ctypes.sizeof(_capi.ConvParams) == 176
+
+
+def test_no_cpu_fallback_and_error_surface(dm1_params):
+    import advshadow_b200
+    from advshadow_b200 import diff_model, ops
+    m, _ = dm1_params
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 32, 32), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        diff_model.GaussianDiffusion().ddim_sample(m, 32, batch_size=1, ddim_timesteps=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.upsample_nearest2x(torch.zeros(1, 2, 2, 8))
+    with pytest.raises(TypeError):
+        diff_model.UNetModel(conv_resample=False)          # reference: nn.AvgPool2d(stride=2) TypeError, dm1:150
+    with pytest.raises(AssertionError):
+        diff_model.UNetModel(model_channels=32, num_heads=3)   # channels % num_heads, dm1:111
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    import diff_model as dropin
+    for n in ["os", "Dataset", "DataLoader", "Image", "transforms", "torch", "UNetModel", "GaussianDiffusion", "tqdm",
+              "plt", "np", "F", "nn", "math"]:
+        assert hasattr(dropin, n), n
