@@ -299,3 +299,65 @@ class UNetEngine:
             self.temb_cur.copy_(table)
             self.run()
             return self.eps.clone()
+
+    # ---- measurement helpers (bench.py) ----
+    def launch_costs(self):
+        """Per launch-list entry: (name, algorithmic flops, algorithmic bytes) -- DESIGN.md section 'rooflines'."""
+        out = []
+        plan, ab = self.plan, self.act_bytes
+        it = iter(self._launches)
+        for op in plan.ops:
+            a = op.args
+            if op.kind == "gn":
+                n = self.B * a["HW"] * a["C"]
+                out.append(("gn_stats", 0, n * ab))                  # one read
+                out.append(("gn_apply", 0, 2 * n * ab))              # one read + one write
+            elif op.kind == "conv":
+                k = sum(plan.shape(s)[3] * taps for (s, _, taps, _) in a["segs"])
+                m = self.B * a["H"] * a["W"]
+                byts = sum(self.B * a["H"] * a["W"] * (a["stride"] ** 2 if i == 0 else 1) * plan.shape(s)[3]
+                           for i, (s, _, _, _) in enumerate(a["segs"])) * ab
+                byts += k * a["cout"] * ab + m * a["cout"] * ab * (2 if a["residual"] else 1)
+                name = "conv_sm100" if self._conv_sm100_ok(a) else "conv_simt"
+                out.append((name, 2 * m * k * a["cout"], byts))
+            elif op.kind == "attn":
+                c = a["heads"] * a["dh"]
+                name = "attn_sm100" if self._attn_sm100_ok(a) else "attn_simt"
+                out.append((name, 4 * self.B * a["T"] * a["T"] * c, 4 * self.B * a["T"] * c * ab))
+            elif op.kind == "up":
+                n = self.B * a["H"] * a["W"] * a["C"]
+                out.append(("upsample", 0, 5 * n * ab))
+            elif op.kind == "stem":
+                m = self.B * a["H"] * a["W"]
+                out.append(("stem", 2 * m * 9 * a["cin"] * a["cout"], m * (a["cin"] * 4 + a["cout"] * ab)))
+            elif op.kind == "head":
+                m = self.B * a["H"] * a["W"]
+                out.append(("head", 2 * m * 9 * a["cin"] * a["cout"], m * (a["cin"] * ab + a["cout"] * 4)))
+        assert len(out) == len(self._launches)
+        return out
+
+    def profile_forward(self, repeats=1):
+        """Run the forward eagerly with a CUDA-event pair around every launch (on the launching stream).
+        Returns {name: dict(ms, flops, bytes, launches)} summed over the forward, averaged over repeats."""
+        costs = self.launch_costs()
+        st = _stream_ptr()
+        agg = {}
+        with torch.cuda.device(self.device):
+            for _ in range(repeats):
+                evs = []
+                for (fn, args, name) in self._launches:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = fn(*args, st)
+                    e1.record()
+                    if rc:
+                        raise capi.AdvsError(f"{name} failed: {self.lib.advs_last_error().decode()}")
+                    evs.append((e0, e1))
+                torch.cuda.synchronize(self.device)
+                for (e0, e1), (name, fl, by) in zip(evs, costs):
+                    d = agg.setdefault(name, dict(ms=0.0, flops=0, bytes=0, launches=0))
+                    d["ms"] += e0.elapsed_time(e1) / repeats
+                    d["flops"] += fl / repeats
+                    d["bytes"] += by / repeats
+                    d["launches"] += 1.0 / repeats
+        return agg

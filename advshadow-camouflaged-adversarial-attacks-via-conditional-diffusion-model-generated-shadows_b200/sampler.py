@@ -1,0 +1,109 @@
+"""ShadowSampler: the end-to-end hot path as one reusable object.
+
+  noise x_T  --DDIM-n (UNet eps, fused update; one captured CUDA graph per step)-->  x_0
+  x_0, clean image, feature mask, (centre, radius)  --fused composite-->  shadowed image
+
+The object owns every device buffer (static addresses => the per-step graph is captured once and
+replayed n times per trajectory, for any number of trajectories).  Reference call sites it replaces:
+GaussianDiffusion.ddim_sample (dm1:416-474) followed by apply_shadow's blend (dm2:642-653).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from ._diffusion import ddim_timestep_tables
+from ._model import UNetModelBase
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ShadowSampler:
+    def __init__(self, model: UNetModelBase, diffusion, batch_size, image_size, ddim_timesteps=50,
+                 ddim_discr_method="uniform", clip_denoised=True, precision=None, mask_channels=1, use_graph=True):
+        if not isinstance(model, UNetModelBase):
+            raise TypeError("ShadowSampler needs an advshadow_b200 UNetModel")
+        self.model, self.gd = model, diffusion
+        self.B, self.S, self.n = batch_size, image_size, ddim_timesteps
+        self.clip = 1 if clip_denoised else 0
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("ShadowSampler runs on CUDA only (no CPU path)")
+        self.C = model.in_channels
+        with torch.cuda.device(self.device):
+            self.eng = model.engine(batch_size, image_size, image_size, precision=precision)
+            seq, prev = ddim_timestep_tables(diffusion.timesteps, ddim_timesteps, ddim_discr_method)
+            self.coef = diffusion.ddim_coefficients(seq, prev, ddim_timesteps, 0.0).to(self.device)
+            ts = torch.tensor([int(seq[i]) for i in reversed(range(ddim_timesteps))], dtype=torch.int64)
+            self.table = self.eng.temb_table(ts)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            shape = (batch_size, self.C, image_size, image_size)
+            self.clean = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self.fmask = torch.zeros(batch_size, mask_channels, image_size, image_size, dtype=torch.float32,
+                                     device=self.device)
+            self.centers = torch.zeros(batch_size, 2, dtype=torch.float32, device=self.device)
+            self.radii = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
+            self.out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self.n_elems = int(np.prod(shape))
+            self.graph = None
+            if use_graph:
+                self._capture()
+        # launches per trajectory: per step select_row + UNet kernels + update + advance; + composite
+        self.launches_per_trajectory = self.n * (self.eng.n_kernels + 3) + 1
+
+    def _one_step(self):
+        eng, st = self.eng, _st()
+        capi.call("advs_select_row", self.table.data_ptr(), self.table.shape[1], self.step_dev.data_ptr(),
+                  eng.temb_cur.data_ptr(), self.B, st)
+        eng.run()
+        capi.call("advs_ddim_step", eng.x.data_ptr(), eng.eps.data_ptr(), None, eng.x.data_ptr(), self.n_elems,
+                  self.coef.data_ptr(), self.step_dev.data_ptr(), 1, self.clip, st)
+
+    def _capture(self):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._one_step()          # eager once: one-time kernel attribute setup must not be captured
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.step_dev.zero_()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._one_step()
+        self.step_dev.zero_()
+
+    def run_device(self):
+        """Trajectory + composite on buffers already resident in HBM (eng.x holds x_T on entry)."""
+        self.step_dev.zero_()
+        for _ in range(self.n):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._one_step()
+        capi.call("advs_shadow_composite_generated", self.clean.data_ptr(), self.eng.x.data_ptr(),
+                  self.centers.data_ptr(), self.radii.data_ptr(), self.fmask.data_ptr(), self.fmask.shape[1],
+                  self.out.data_ptr(), self.B, self.C, self.S, self.S, _st())
+        return self.out
+
+    def set_inputs(self, x_T, clean, fmask, centers, radii, non_blocking=True):
+        """Copy one batch (host or device tensors) into the static buffers."""
+        self.eng.x.copy_(x_T, non_blocking=non_blocking)
+        self.clean.copy_(clean, non_blocking=non_blocking)
+        self.fmask.copy_(fmask, non_blocking=non_blocking)
+        self.centers.copy_(centers, non_blocking=non_blocking)
+        self.radii.copy_(radii, non_blocking=non_blocking)
+
+    @torch.no_grad()
+    def __call__(self, x_T, clean, fmask, centers, radii, out_host=None):
+        """Host in, host out: H2D of the batch, n DDIM steps, composite, D2H of the shadowed images."""
+        with torch.cuda.device(self.device):
+            self.set_inputs(x_T, clean, fmask, centers, radii)
+            out = self.run_device()
+            if out_host is None:
+                return out.cpu()
+            out_host.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return out_host
