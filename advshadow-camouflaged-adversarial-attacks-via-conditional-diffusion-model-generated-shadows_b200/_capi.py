@@ -33,7 +33,7 @@ class ConvParams(C.Structure):
         ("residual", C.c_void_p), ("y", C.c_void_p),
         ("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p),
         ("heads", C.c_int32), ("qk_scale", C.c_float),
-        ("dtype", C.c_int32), ("reserved", C.c_int32),
+        ("dtype", C.c_int32), ("cout_valid", C.c_int32),
     ]
 
 

@@ -34,6 +34,10 @@ int validate_conv(const advs_conv_params* p, const char* who) {
     ADVS_CHECK_ARG(p->q && p->k && p->vt, "%s: q/k/vt null in qkv mode", who);
     ADVS_CHECK_ARG(p->heads > 0 && p->Cout % (3 * p->heads) == 0, "%s: Cout not 3*heads*dh", who);
     ADVS_CHECK_ARG(p->residual == nullptr, "%s: residual unsupported in qkv mode", who);
+  } else if (p->out_mode == 2) {
+    ADVS_CHECK_ARG(p->y != nullptr, "%s: y is null", who);
+    ADVS_CHECK_ARG(p->cout_valid > 0 && p->cout_valid <= p->Cout, "%s: cout_valid out of range", who);
+    ADVS_CHECK_ARG(p->residual == nullptr, "%s: residual unsupported in NCHW output mode", who);
   } else {
     ADVS_CHECK_ARG(false, "%s: bad out_mode", who);
   }

@@ -74,7 +74,13 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// bf16-mode SiLU: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- one MUFU op (tanh.approx, rel. err 2^-11,
+// below bf16 resolution) instead of ex2 + rcp; GN+SiLU is MUFU-bound otherwise.
+__device__ __forceinline__ float silu_f(float x) {
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 // accurate variant (fp32 parity mode): expf instead of the fast intrinsic
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
 
@@ -105,6 +111,7 @@ struct EpilogueParams {
   float qk_scale;
   int HW;    // pixels per image (T for attention)
   int Cout;
+  int cout_valid;  // out_mode 2: real output channels
 };
 
 inline EpilogueParams make_epilogue(const advs_conv_params& p) {
@@ -123,6 +130,7 @@ inline EpilogueParams make_epilogue(const advs_conv_params& p) {
   e.qk_scale = p.qk_scale;
   e.HW = p.H * p.W;
   e.Cout = p.Cout;
+  e.cout_valid = (p.out_mode == 2) ? p.cout_valid : p.Cout;
   return e;
 }
 

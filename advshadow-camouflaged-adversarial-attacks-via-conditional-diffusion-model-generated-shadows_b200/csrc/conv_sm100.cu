@@ -113,6 +113,11 @@ __device__ __forceinline__ void epilogue_store32(const EpilogueParams& e, const 
       o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
       yp[j] = o;
     }
+  } else if (e.out_mode == 2) {
+    float* dst = reinterpret_cast<float*>(e.y) + ((size_t)b * e.cout_valid + n) * e.HW + t;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < e.cout_valid) dst[(size_t)j * e.HW] = v[j];
   } else {
     const int head = n / (3 * e.dh);
     const int r = n - head * 3 * e.dh;
@@ -273,7 +278,8 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
         tmem_ld_32x32b_x32(taddr + chunk * 32, r);
         tmem_wait_ld();
         const int n = n_tile * BN + chunk * 32;
-        if (valid && n < a.Cout) epilogue_store32(a.epi, r, m, b, t, n);
+        if (n >= a.epi.cout_valid) break;   // zero-padded output channels (uniform across the warp)
+        if (valid) epilogue_store32(a.epi, r, m, b, t, n);
       }
       tc_fence_before();
       __syncwarp();

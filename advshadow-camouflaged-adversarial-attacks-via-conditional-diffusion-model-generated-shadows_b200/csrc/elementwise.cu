@@ -53,39 +53,68 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------
-// stem: x NCHW fp32 (Cin small) -> y NHWC T.  thread = (pixel, 8 couts); weights in smem.
-template <typename T>
-__global__ void k_conv3x3_stem(const float* __restrict__ x, const float* __restrict__ w,
-                               const float* __restrict__ bias, T* __restrict__ y, int B, int H, int W,
-                               int Cin, int Cout) {
-  extern __shared__ float sw[];  // [Cout][9*Cin]
+// stem: x NCHW fp32 (Cin small) -> y NHWC T.  One thread = one pixel x CPT output channels:
+// the 9*Cin inputs sit in registers (coalesced NCHW loads: consecutive lanes = consecutive pixels),
+// weights are read from smem as warp-wide broadcasts ([k][cout] layout, float4 per load).
+template <typename T, int CPT, int KMAX>
+__global__ void __launch_bounds__(128) k_conv3x3_stem(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, T* __restrict__ y, int B, int H,
+                                                      int W, int Cin, int Cout) {
+  extern __shared__ float sw[];  // [9*Cin][Cout]
   const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) sw[i] = w[i];
+  for (int j = threadIdx.x; j < Cout * K; j += blockDim.x) {  // conflict-free smem stores
+    int k = j / Cout, o = j - k * Cout;
+    sw[j] = w[o * K + k];
+  }
   __syncthreads();
-  const int cg = Cout / 8;
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)B * H * W * cg;
-  if (idx >= total) return;
-  int j = (int)(idx % cg);
-  size_t p = idx / cg;
+  const size_t total = (size_t)B * H * W;
+  const int cbase = blockIdx.y * CPT;
+  for (int it = 0; it < 8; ++it) {
+  size_t p = ((size_t)blockIdx.x * 8 + it) * blockDim.x + threadIdx.x;
+  if (p >= total) return;
   int wo = (int)(p % W);
   int ho = (int)((p / W) % H);
   int b = (int)(p / ((size_t)W * H));
-  float acc[8];
+  float xin[KMAX];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = bias ? bias[j * 8 + i] : 0.f;
+  for (int k = 0; k < KMAX; ++k) xin[k] = 0.f;
+#pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     int hi = ho + tap / 3 - 1, wi = wo + tap % 3 - 1;
-    if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
-    for (int c = 0; c < Cin; ++c) {
-      float xv = x[(((size_t)b * Cin + c) * H + hi) * W + wi];
+    bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, sw[(j * 8 + i) * K + tap * Cin + c], acc[i]);
+    for (int c = 0; c < KMAX / 9; ++c)
+      if (c < Cin && ok) xin[tap * (KMAX / 9) + c] = x[(((size_t)b * Cin + c) * H + hi) * W + wi];
+  }
+  float acc[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) acc[i] = bias ? bias[cbase + i] : 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+    for (int c = 0; c < KMAX / 9; ++c) {
+      if (c < Cin) {
+        const float xv = xin[tap * (KMAX / 9) + c];
+        const float4* wr = reinterpret_cast<const float4*>(sw + (tap * Cin + c) * Cout + cbase);
+#pragma unroll
+        for (int i = 0; i < CPT / 4; ++i) {
+          float4 w4 = wr[i];
+          acc[4 * i] = fmaf(xv, w4.x, acc[4 * i]);
+          acc[4 * i + 1] = fmaf(xv, w4.y, acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(xv, w4.z, acc[4 * i + 2]);
+          acc[4 * i + 3] = fmaf(xv, w4.w, acc[4 * i + 3]);
+        }
+      }
     }
   }
-  Vec8<T> v;
-  v.from_float(acc);
-  v.store(y + p * Cout + j * 8);
+  T* yp = y + p * Cout + cbase;
+#pragma unroll
+  for (int i = 0; i < CPT / 8; ++i) {
+    Vec8<T> v;
+    v.from_float(acc + 8 * i);
+    v.store(yp + 8 * i);
+  }
+  }
 }
 
 // head: x NHWC T -> y NCHW fp32 (Cout small, <= 4). one warp per pixel, lanes split channels.
@@ -267,15 +296,15 @@ int advs_pack_conv_weight(const float* w, void* dst, int O, int I, int kh, int k
 int advs_conv3x3_stem(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cin,
                       int Cout, int dtype, void* stream) {
   ADVS_CHECK_ARG(x && w && y && B > 0 && H > 0 && W > 0, "conv3x3_stem: bad args");
-  ADVS_CHECK_ARG(Cout % 8 == 0 && Cin >= 1 && Cin <= 16, "conv3x3_stem: needs Cout%%8==0 and Cin<=16");
+  ADVS_CHECK_ARG(Cout % 32 == 0 && Cin >= 1 && Cin <= 4, "conv3x3_stem: needs Cout%%32==0 and Cin<=4");
   size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
   ADVS_CHECK_ARG(smem <= 48 * 1024, "conv3x3_stem: weights exceed 48 KB of shared memory");
-  size_t total = (size_t)B * H * W * (Cout / 8);
-  unsigned blocks = (unsigned)((total + 255) / 256);
+  size_t total = (size_t)B * H * W;
+  dim3 grid((unsigned)((total + 1023) / 1024), Cout / 32);
   if (dtype == ADVS_F32)
-    k_conv3x3_stem<float><<<blocks, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (float*)y, B, H, W, Cin, Cout);
+    k_conv3x3_stem<float, 32, 36><<<grid, 128, smem, (cudaStream_t)stream>>>(x, w, bias, (float*)y, B, H, W, Cin, Cout);
   else
-    k_conv3x3_stem<__nv_bfloat16><<<blocks, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Cin, Cout);
+    k_conv3x3_stem<__nv_bfloat16, 32, 36><<<grid, 128, smem, (cudaStream_t)stream>>>(x, w, bias, (__nv_bfloat16*)y, B, H, W, Cin, Cout);
   ADVS_CHECK_LAUNCH("conv3x3_stem");
   return ADVS_OK;
 }

@@ -13,6 +13,8 @@ __device__ __forceinline__ void epilogue_store1(const EpilogueParams& e, size_t 
   if (e.out_mode == 0) {
     if (e.residual) v += to_f(reinterpret_cast<const T*>(e.residual)[m * e.Cout + n]);
     reinterpret_cast<T*>(e.y)[m * e.Cout + n] = from_f<T>(v);
+  } else if (e.out_mode == 2) {
+    if (n < e.cout_valid) reinterpret_cast<float*>(e.y)[((size_t)b * e.cout_valid + n) * e.HW + t] = v;
   } else {
     int head = n / (3 * e.dh);
     int r = n - head * 3 * e.dh;

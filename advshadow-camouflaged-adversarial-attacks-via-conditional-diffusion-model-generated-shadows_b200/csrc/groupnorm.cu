@@ -17,8 +17,8 @@ struct GnGeom {
 };
 
 static GnGeom gn_geom(int B, int HW) {
-  // aim for >= 4 CTAs per SM over the whole launch, chunks of at least 64 pixels
-  int want = (148 * 4 + B - 1) / B;
+  // aim for >= 16 CTAs per SM over the whole launch, chunks of at least 64 pixels
+  int want = (148 * 16 + B - 1) / B;
   int max_chunks = (HW + 63) / 64;
   int chunks = want < max_chunks ? want : max_chunks;
   if (chunks < 1) chunks = 1;
@@ -49,7 +49,23 @@ __global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
   if (active) {
     const T* base = x + ((size_t)b * HW) * C + j * 8;
-    for (int p = p0 + pl; p < p1; p += ppi) {
+    int p = p0 + pl;
+    for (; p + 3 * ppi < p1; p += 4 * ppi) {   // 4 independent 16-byte loads in flight per thread
+      Vec8<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u].load(base + (size_t)(p + u * ppi) * C);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        v[u].to_float(f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          ss[i] = fmaf(f[i], f[i], ss[i]);
+        }
+      }
+    }
+    for (; p < p1; p += ppi) {
       Vec8<T> v;
       v.load(base + (size_t)p * C);
       float f[8];
@@ -122,38 +138,63 @@ __global__ void k_gn_finalize(const float* __restrict__ part, int chunks, int Ct
   }
 }
 
+// thread = one 8-channel vector position, looping over the pixels of its chunk: the 16 scale/shift
+// floats stay in registers, so the stream is exactly one 16-byte load + one 16-byte store per vector.
 template <typename T, bool SILU>
-__global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict__ x1, int c1, int HW, size_t npix,
-                           const float* __restrict__ scale_shift, T* __restrict__ y) {
+__global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict__ x1, int c1, int HW,
+                           int pix_per_chunk, const float* __restrict__ scale_shift, T* __restrict__ y) {
   const int Ctot = c0 + c1;
   const int cv = Ctot / 8;
-  size_t total = npix * cv;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    int j = (int)(idx % cv);
-    size_t p = idx / cv;
-    int b = (int)(p / HW);
-    int c = j * 8;
-    Vec8<T> v;
-    if (c < c0) v.load(x0 + p * c0 + c);
-    else v.load(x1 + p * c1 + (c - c0));
-    float f[8];
-    v.to_float(f);
+  const int ppi = blockDim.x / cv;
+  const int pl = threadIdx.x / cv;
+  const int j = threadIdx.x % cv;
+  if (pl >= ppi) return;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_chunk;
+  int p1 = p0 + pix_per_chunk;
+  if (p1 > HW) p1 = HW;
+  const int c = j * 8;
+  float sc[8], sh[8];
+  {
     const float4* ab = reinterpret_cast<const float4*>(scale_shift + ((size_t)b * Ctot + c) * 2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float4 t = __ldg(ab + i);
-      float a = fmaf(f[2 * i], t.x, t.y);
-      float d = fmaf(f[2 * i + 1], t.z, t.w);
-      if (SILU) {
-        if constexpr (sizeof(T) == 4) { a = silu_acc(a); d = silu_acc(d); }
-        else { a = silu_f(a); d = silu_f(d); }
-      }
-      f[2 * i] = a;
-      f[2 * i + 1] = d;
+      sc[2 * i] = t.x; sh[2 * i] = t.y; sc[2 * i + 1] = t.z; sh[2 * i + 1] = t.w;
     }
-    v.from_float(f);
-    v.store(y + p * Ctot + c);
+  }
+  const bool first = c < c0;
+  const T* src = first ? x0 + ((size_t)b * HW) * c0 + c : x1 + ((size_t)b * HW) * c1 + (c - c0);
+  const int cs = first ? c0 : c1;
+  T* dst = y + ((size_t)b * HW) * Ctot + c;
+  auto body = [&](const Vec8<T>& vin, int p) {
+    float f[8];
+    vin.to_float(f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = fmaf(f[i], sc[i], sh[i]);
+      if (SILU) {
+        if constexpr (sizeof(T) == 4) a = silu_acc(a);
+        else a = silu_f(a);
+      }
+      f[i] = a;
+    }
+    Vec8<T> vo;
+    vo.from_float(f);
+    vo.store(dst + (size_t)p * Ctot);
+  };
+  int p = p0 + pl;
+  for (; p + 3 * ppi < p1; p += 4 * ppi) {
+    Vec8<T> v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u].load(src + (size_t)(p + u * ppi) * cs);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(v[u], p + u * ppi);
+  }
+  for (; p < p1; p += ppi) {
+    Vec8<T> v;
+    v.load(src + (size_t)p * cs);
+    body(v, p);
   }
 }
 
@@ -188,14 +229,14 @@ static int gn_stats_impl(const void* x0, int c0, const void* x1, int c1, int B, 
 template <typename T>
 static int gn_apply_impl(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* ss, int silu,
                          void* y, cudaStream_t st) {
-  size_t npix = (size_t)B * HW;
-  size_t total = npix * ((c0 + c1) / 8);
-  size_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;
+  GnGeom g = gn_geom(B, HW);
+  int cv = (c0 + c1) / 8;
+  int threads = cv <= 256 ? 256 : 1024;
+  dim3 grid(g.chunks, B);
   if (silu)
-    k_gn_apply<T, true><<<(unsigned)blocks, 256, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, npix, ss, (T*)y);
+    k_gn_apply<T, true><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y);
   else
-    k_gn_apply<T, false><<<(unsigned)blocks, 256, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, npix, ss, (T*)y);
+    k_gn_apply<T, false><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y);
   ADVS_CHECK_LAUNCH("groupnorm_apply");
   return ADVS_OK;
 }
@@ -234,6 +275,7 @@ int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, 
   ADVS_CHECK_ARG(x0 && c0 > 0 && B > 0 && HW > 0 && scale_shift && y, "groupnorm_apply: bad args");
   if (!x1) c1 = 0;
   ADVS_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm_apply: channel counts must be multiples of 8");
+  ADVS_CHECK_ARG((c0 + c1) / 8 <= 1024, "groupnorm_apply: at most 8192 channels");
   if (dtype == ADVS_F32) return gn_apply_impl<float>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
   if (dtype == ADVS_BF16) return gn_apply_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
   ADVS_CHECK_ARG(false, "groupnorm_apply: bad dtype");

@@ -91,6 +91,9 @@ class UNetEngine:
             return False
         return True
 
+    def _head_sm100_ok(self, a):
+        return self.conv_impl == "sm100" and a["cin"] % 64 == 0 and a["cout"] <= 64
+
     def _ptr(self, buf):
         return self.arena.data_ptr() + self.plan.bufs[buf].offset
 
@@ -107,9 +110,15 @@ class UNetEngine:
         spec = self.spec
         for op in self.plan.ops:
             a = op.args
-            if op.kind in ("stem", "head"):
+            if op.kind == "stem":
                 self._packed[(a["weight"], None)] = torch.empty(a["cout"], 9, a["cin"], dtype=torch.float32, device=dev)
                 self._bias[(a["weight"],)] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
+            elif op.kind == "head":
+                # the head runs through the implicit-GEMM conv (fp32 NCHW epilogue); on the tcgen05 path
+                # its 3 output channels are zero-padded to one 64-row weight tile
+                pad = 64 if self._head_sm100_ok(a) else a["cout"]
+                self._packed[(a["weight"], None)] = torch.zeros(pad, 9, a["cin"], dtype=tdt, device=dev)
+                self._bias[(a["weight"],)] = torch.zeros(pad, dtype=torch.float32, device=dev)
             elif op.kind == "conv":
                 for (src, wname, taps, sl) in a["segs"]:
                     c = self.plan.shape(src)[3]
@@ -139,7 +148,7 @@ class UNetEngine:
                 w = p32(wname + ".weight")
                 if sl is not None:
                     w = w[:, sl[0]:sl[1]].contiguous()
-                O, I, kh, kw = w.shape
+                O, I, kh, kw = w.shape          # dst may have more (zero) rows than O: the padded head
                 dt = capi.F32 if dst.dtype == torch.float32 else capi.BF16
                 capi.call("advs_pack_conv_weight", w.data_ptr(), dst.data_ptr(), O, I, kh, kw, dt, st)
                 self._keep.append(w)
@@ -147,7 +156,7 @@ class UNetEngine:
                 acc = p32(names[0] + ".bias").clone()
                 for n in names[1:]:
                     acc += p32(n + ".bias")
-                dst.copy_(acc)
+                dst[:acc.numel()].copy_(acc)          # (head bias may be zero-padded)
             off = 0
             for slot in self.plan.temb_slots:
                 self.temb_w[off:off + slot.cout].copy_(p32(slot.weight + ".weight"))
@@ -181,8 +190,20 @@ class UNetEngine:
                 self.n_kernels += 1
             elif op.kind == "head":
                 w, b = self._packed[(a["weight"], None)], self._bias[(a["weight"],)]
-                L.append((lib.advs_conv3x3_head, (self._ptr(a["src"]), w.data_ptr(), b.data_ptr(), self.eps.data_ptr(),
-                                                  B, a["H"], a["W"], a["cin"], a["cout"], dt), "head"))
+                cp = capi.ConvParams()
+                cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], w.shape[0], 1, 1
+                cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = self._ptr(a["src"]), w.data_ptr(), a["cin"], 9
+                cp.bias = b.data_ptr()
+                cp.out_mode, cp.y, cp.cout_valid, cp.dtype = 2, self.eps.data_ptr(), a["cout"], dt
+                self._keep.append(cp)
+                if self._head_sm100_ok(a):
+                    pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+                    with torch.cuda.device(self.device):
+                        capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+                    self._plans.append(pb)
+                    L.append((lib.advs_conv_sm100_launch, (pb.ptr,), "head_sm100"))
+                else:
+                    L.append((lib.advs_conv_simt, (C.byref(cp),), "head_simt"))
                 self.n_kernels += 1
             elif op.kind == "gn":
                 srcs = a["srcs"]
@@ -332,7 +353,8 @@ class UNetEngine:
                 out.append(("stem", 2 * m * 9 * a["cin"] * a["cout"], m * (a["cin"] * 4 + a["cout"] * ab)))
             elif op.kind == "head":
                 m = self.B * a["H"] * a["W"]
-                out.append(("head", 2 * m * 9 * a["cin"] * a["cout"], m * (a["cin"] * ab + a["cout"] * 4)))
+                out.append(("head_sm100" if self._head_sm100_ok(a) else "head_simt",
+                            2 * m * 9 * a["cin"] * a["cout"], m * (a["cin"] * ab + a["cout"] * 4)))
         assert len(out) == len(self._launches)
         return out
 

@@ -92,7 +92,9 @@ int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, 
  *                    the block input is the virtual concat [h, skip], dm1:265).
  * out_mode 0: y NHWC [B,H,W,Cout].
  * out_mode 1: "qkv split" for AttentionBlock (dm1:114,120-121): cout = head*3*dh + which*dh + d;
- *             q,k -> [B,heads,T,dh] multiplied by qk_scale (= dh^-1/4), v -> vt [B,heads,dh,T]. */
+ *             q,k -> [B,heads,T,dh] multiplied by qk_scale (= dh^-1/4), v -> vt [B,heads,dh,T].
+ * out_mode 2: y is fp32 NCHW [B,cout_valid,H,W] (the UNet head, dm1:240-243): only the first
+ *             cout_valid output channels are stored; Cout may be zero-padded up to the GEMM tile. */
 typedef struct advs_conv_seg {
   const void* x; /* NHWC [B, Hin, Win, C]; Hin = H*stride for segment 0, H otherwise */
   const void* w; /* [Cout][taps][C] in dtype */
@@ -109,7 +111,7 @@ typedef struct advs_conv_params {
   const float* bias;      /* [Cout] or NULL */
   const float* temb;      /* [B or 1][temb_stride] or NULL: per-image per-channel bias (dm1:101) */
   int32_t temb_stride;    /* floats between images; 0 = broadcast one row */
-  int32_t out_mode;       /* 0 NHWC, 1 qkv split */
+  int32_t out_mode;       /* 0 NHWC, 1 qkv split, 2 fp32 NCHW */
   const void* residual;   /* NHWC [B,H,W,Cout] or NULL */
   void* y;                /* out_mode 0 */
   void* q;                /* out_mode 1 */
@@ -118,7 +120,7 @@ typedef struct advs_conv_params {
   int32_t heads;
   float qk_scale;
   int32_t dtype;
-  int32_t reserved;
+  int32_t cout_valid;     /* out_mode 2: number of real output channels (<= Cout) */
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */

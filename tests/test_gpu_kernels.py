@@ -180,3 +180,60 @@ def test_success_flags(ops):
     ref = (logits.argmax(1) != labels)
     assert torch.equal(flags.bool(), ref)
     assert counts.tolist() == [int(ref.sum()), 300]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 6e-3)])
+def test_stem_conv(ops, dtype, tol):
+    """Cin=3 stem (dm1:192) through advs_conv3x3_stem: fp32 NCHW in, NHWC out."""
+    import ctypes as C
+    from advshadow_b200 import _capi as capi
+    torch.manual_seed(8)
+    B, H, W, cin, cout = 2, 19, 23, 3, 128
+    x = torch.randn(B, cin, H, W, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") / 5
+    b = torch.randn(cout, device="cuda")
+    wp = ops.pack_conv_weight(w, torch.float32)
+    y = torch.empty(B, H, W, cout, dtype=dtype, device="cuda")
+    capi.call("advs_conv3x3_stem", x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), B, H, W, cin, cout,
+              capi.F32 if dtype == torch.float32 else capi.BF16, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    ref = F.conv2d(x, w, b, padding=1)
+    assert rel_err(nchw(y), ref) < tol
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 2e-5), ("sm100", torch.bfloat16, 1e-2)])
+def test_head_conv_nchw_f32_output(ops, impl, dtype, tol):
+    """UNet head (dm1:240-243): 128 -> 3 channels through the implicit GEMM with the fp32 NCHW epilogue;
+    on the tcgen05 path the 3 output channels are zero-padded to a 64-row weight tile."""
+    import ctypes as C
+    from advshadow_b200 import _capi as capi
+    torch.manual_seed(9)
+    B, H, W, cin, cout = 2, 16, 32, 128, 3
+    x = torch.randn(B, H, W, cin, device="cuda").to(dtype)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / 30).to(dtype).float()
+    bias = torch.randn(cout, device="cuda")
+    pad = 64 if impl == "sm100" else cout
+    wp = torch.zeros(pad, 9, cin, dtype=dtype, device="cuda")
+    wp[:cout] = ops.pack_conv_weight(w, dtype)
+    bp = torch.zeros(pad, device="cuda")
+    bp[:cout] = bias
+    y = torch.full((B, cout, H, W), float("nan"), device="cuda")
+    cp = capi.ConvParams()
+    cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, pad, 1, 1
+    cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), wp.data_ptr(), cin, 9
+    cp.bias, cp.out_mode, cp.y, cp.cout_valid = bp.data_ptr(), 2, y.data_ptr(), cout
+    cp.dtype = capi.F32 if dtype == torch.float32 else capi.BF16
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if impl == "simt":
+        capi.call("advs_conv_simt", C.byref(cp), st)
+    else:
+        pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+        capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+        capi.call("advs_conv_sm100_launch", pb.ptr, st)
+    ref = conv_ref(x, w, 1, bias)
+    assert rel_err(y, ref) < tol
+    # the dedicated bandwidth kernel of the C ABI computes the same thing
+    y2 = torch.empty_like(y)
+    w32 = ops.pack_conv_weight(w, torch.float32)
+    capi.call("advs_conv3x3_head", x.data_ptr(), w32.data_ptr(), bias.data_ptr(), y2.data_ptr(), B, H, W, cin, cout,
+              cp.dtype, st)
+    assert rel_err(y2, ref) < tol
