@@ -1,0 +1,105 @@
+"""Data-parallel attack-loop harness: shard images (and shadow candidates) over the GPUs of one box,
+sample + composite on each shard, let the PyTorch victim judge, exchange per-image success flags and
+ASR counts.
+
+The reference has no such loop in one place; the pieces are compute_asr's decision rule
+(ASR_fast.py:101-126: argmax -> int_to_label != filename.rsplit('_', 1)[0]), the id2label JSON maps
+(config*.json) and the per-image Python loops of ddim2/main2.py:159-168.  Images and candidates are
+independent trajectories, so the path shards with NO collective inside the step loop; the only
+exchange is one all_gather(uint8 flags) + one all_reduce(int64[2] counts) per batch.
+"""
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+# ---- label plumbing (bit-exact string handling) ----
+def label_from_filename(filename: str) -> str:
+    """True label = text before the LAST underscore (ASR_fast.py:109), e.g. american_bulldog_12.jpg."""
+    return filename.rsplit('_', 1)[0]
+
+
+def load_id2label(path: str) -> Tuple[Dict[int, str], Dict[str, int]]:
+    """config.json / configvit.json format: {"id2label": {"0": "Abyssinian", ...}} (ASR_fast.py:67-75)."""
+    with open(path, 'r') as f:
+        data = json.load(f)
+    id2label = data['id2label']
+    label_to_int = {label: int(i) for i, label in id2label.items()}
+    int_to_label = {v: k for k, v in label_to_int.items()}
+    return int_to_label, label_to_int
+
+
+def filenames_to_label_ids(filenames: Sequence[str], label_to_int: Dict[str, int]) -> List[int]:
+    """Unknown labels map to -1: argmax can never equal it, so such an image always counts as a success,
+    exactly like `predicted_label != true_label` does in the reference."""
+    return [label_to_int.get(label_from_filename(f), -1) for f in filenames]
+
+
+# ---- sharding ----
+def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of rank `rank`; the first n_items % world ranks get one extra item."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def fold_candidates(flags: torch.Tensor, candidates: int) -> torch.Tensor:
+    """[B*K] per-candidate flags -> [B] per-image flags: an image is broken if any candidate breaks it."""
+    if candidates == 1:
+        return flags
+    return flags.view(-1, candidates).amax(dim=1)
+
+
+def exchange_success(flags_local: torch.Tensor, group=None, pad_to: Optional[int] = None):
+    """The path's only collective.  flags_local: uint8 [B_local] on any device (NCCL on GPUs, gloo on CPU
+    in the tests).  Returns (flags_all uint8 [sum B_local], counts int64 [2] = {successes, total}).
+    Shards may be ragged: they are padded to `pad_to` (default: max over ranks) with 255 and trimmed."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    counts = torch.stack([flags_local.sum(dtype=torch.int64),
+                          torch.tensor(flags_local.numel(), dtype=torch.int64, device=flags_local.device)])
+    if world == 1:
+        return flags_local.clone(), counts
+    n_local = torch.tensor([flags_local.numel()], dtype=torch.int64, device=flags_local.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    width = pad_to or max(sizes)
+    padded = torch.full((width,), 255, dtype=torch.uint8, device=flags_local.device)
+    padded[:flags_local.numel()] = flags_local
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    dist.all_reduce(counts, group=group)
+    return torch.cat([g[:n] for g, n in zip(gathered, sizes)]), counts
+
+
+def victim_preprocess(images: torch.Tensor, size: int = 224) -> torch.Tensor:
+    """Resize((224,224)) + ToTensor with NO normalisation (ASR_fast.py:90-97): [0,1] tensors in, out."""
+    if images.shape[-1] == size and images.shape[-2] == size:
+        return images
+    return F.interpolate(images, size=(size, size), mode="bilinear", antialias=True, align_corners=False)
+
+
+class AttackLoop:
+    """One rank of the sharded attack loop.  `sampler` is a ShadowSampler for this rank's local batch
+    (B_local * candidates trajectories); `victim` is any PyTorch classifier returning [N, classes] logits
+    (HF models: pass `lambda x: model(x).logits`)."""
+
+    def __init__(self, sampler, victim, candidates: int = 1, victim_size: int = 224, group=None):
+        self.sampler, self.victim, self.K, self.victim_size, self.group = sampler, victim, candidates, victim_size, group
+
+    @torch.no_grad()
+    def step(self, x_T, clean, fmask, centers, radii, labels):
+        """All inputs are this rank's shard, already expanded to B_local*K candidate rows
+        (candidate = (noise seed, shadow radius) pair).  labels: int64 [B_local*K]."""
+        from . import ops
+        self.sampler.set_inputs(x_T, clean, fmask, centers, radii)
+        shadowed = self.sampler.run_device()
+        logits = self.victim(victim_preprocess(shadowed, self.victim_size)).float()
+        flags, _ = ops.success_flags(logits, labels.to(logits.device))
+        flags = fold_candidates(flags, self.K)
+        flags_all, counts = exchange_success(flags, self.group)
+        return {"shadowed": shadowed, "flags_local": flags, "flags": flags_all, "successes": int(counts[0]),
+                "total": int(counts[1]), "asr": float(counts[0]) / max(int(counts[1]), 1)}

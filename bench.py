@@ -19,6 +19,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH = 2.04e9   # profiles/r01_summary.md (6 launches of k_conv_sm100<256>, batch 64)
 METRIC = "shadowed images/sec (DDIM-50, 256x256)"
 UNIT = "images/s"
 
@@ -140,6 +141,7 @@ def main():
     import advshadow_b200  # noqa: F401
     from advshadow_b200 import diff_model2, ops
     from advshadow_b200.sampler import ShadowSampler
+    from advshadow_b200.attack import exchange_success
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -174,12 +176,9 @@ def main():
 
     def exchange():
         # the path's only collective: per-image success flags + ASR counts, once per batch
-        flags, counts = ops.success_flags(logits, labels)
-        if world > 1:
-            allf = torch.empty(world * B, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(allf, flags)
-            dist.all_reduce(counts)
-        return counts
+        # (synthetic victim logits: the victim network itself stays PyTorch and is not part of this metric)
+        flags, _ = ops.success_flags(logits, labels)
+        return exchange_success(flags, pad_to=B)[1]
 
     def barrier():
         if world > 1:
@@ -251,7 +250,10 @@ def main():
             "gpu_launches": sampler.launches_per_trajectory * args.steps + args.steps,
             "roofline": {"kernel": "k_conv_sm100 (tcgen05 implicit-GEMM conv, all launches of one UNet forward)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         "traffic": None, "peak_source": peak_src},
+                         # mean dram__bytes_read+write per captured conv launch, profiles/prof_r01_key_metrics.csv
+                         "traffic": NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH,
+                         "algorithmic_bytes_per_launch": conv["bytes"] / max(conv["launches"], 1),
+                         "peak_source": peak_src},
             "whole_path_tensor_frac": value / world * flops_per_img / 1e12 / peak_tf,
             "forward_breakdown": breakdown, "hbm_peak_gbs": peak_bw,
         }
