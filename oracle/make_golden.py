@@ -145,6 +145,51 @@ def shadow_cases():
     return cases
 
 
+def stochastic_cases():
+    """DDPM ancestral `sample` (dm1:356-413, what main.py:124 calls) and DDIM with eta>0, with the
+    reference's torch.randn / randn_like draws replaced by recorded tensors."""
+    dm1 = R.dm1()
+    torch.manual_seed(0)
+    model = dm1.UNetModel().eval()
+    g = torch.Generator().manual_seed(99)
+    out = {}
+
+    class Feed:
+        def __init__(self, real, tensors):
+            self.real, self.it = real, iter(tensors)
+
+        def __getattr__(self, k):
+            return getattr(self.real, k)
+
+        def randn(self, *a, **k):
+            return next(self.it).clone()
+
+        def randn_like(self, x, *a, **k):
+            return next(self.it).clone()
+
+    # DDPM, T = 20
+    T = 20
+    gd = dm1.GaussianDiffusion(timesteps=T)
+    draws = [torch.randn(1, 3, 32, 32, generator=g) for _ in range(T + 1)]     # x_T, then one z per step
+    saved = dm1.torch
+    dm1.torch = Feed(saved, draws)
+    try:
+        imgs = gd.sample(model, 32, batch_size=1, channels=3)
+    finally:
+        dm1.torch = saved
+    out["ddpm"] = dict(T=T, x_T=draws[0], noise=torch.stack(draws[1:]), traj=torch.from_numpy(np.stack(imgs)))
+    # DDIM eta = 0.5, 5 steps of T = 1000
+    gd = dm1.GaussianDiffusion(timesteps=1000)
+    draws = [torch.randn(2, 3, 32, 32, generator=g) for _ in range(6)]
+    dm1.torch = Feed(saved, draws)
+    try:
+        img = gd.ddim_sample(model, 32, batch_size=2, channels=3, ddim_timesteps=5, ddim_eta=0.5)
+    finally:
+        dm1.torch = saved
+    out["ddim_eta"] = dict(x_T=draws[0], noise=torch.stack(draws[1:]), final=torch.from_numpy(img), eta=0.5, n=5)
+    return out
+
+
 def schedules():
     dm1, dm2 = R.dm1(), R.dm2()
     out = {}
@@ -160,5 +205,6 @@ if __name__ == "__main__":
     torch.save(forwards(), os.path.join(OUT, "forwards.pt"))
     torch.save(shadow_cases(), os.path.join(OUT, "shadow.pt"))
     torch.save(schedules(), os.path.join(OUT, "schedules.pt"))
+    torch.save(stochastic_cases(), os.path.join(OUT, "stochastic.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

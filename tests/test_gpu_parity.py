@@ -211,3 +211,68 @@ def test_foreign_callable_model_uses_fused_update(pkg, golden):
         x0 = torch.clamp((x - torch.sqrt(1. - a_t) * e) / torch.sqrt(a_t), -1., 1.)
         x = torch.sqrt(a_p) * x0 + torch.sqrt(1 - a_p) * e
     assert np.allclose(out, x.cpu().numpy(), atol=1e-6)
+
+
+def test_ddpm_sample_matches_reference(pkg, golden):
+    """§8(f) row 1: the DDPM ancestral loop main.py:124 calls (dm1:356-413), noise injected, fp32 mode.
+    Return type: list of T numpy arrays like the reference; every step is compared."""
+    g = golden("stochastic.pt")["ddpm"]
+    model, _ = get_model(pkg, "dm1")
+    model.set_precision("fp32")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=g["T"])
+    imgs = gd.sample(model, 32, batch_size=1, channels=3, x_T=g["x_T"], noise=list(g["noise"]))
+    assert isinstance(imgs, list) and len(imgs) == g["T"] and imgs[-1].shape == (1, 3, 32, 32)
+    err = max(float(np.abs(imgs[i] - g["traj"][i].numpy()).max()) for i in range(g["T"]))
+    print(f"DDPM T={g['T']} trajectory max|err| = {err:.3e}")
+    assert err <= TOL_FP32
+    last = gd.sample(model, 32, batch_size=1, channels=3, x_T=g["x_T"], noise=list(g["noise"]), keep="last")
+    assert np.array_equal(last[-1], imgs[-1])
+    with pytest.raises(IndexError):
+        last[0]
+    model.set_precision("bf16")
+    model.release_engines()
+
+
+def test_ddim_eta_matches_reference(pkg, golden):
+    g = golden("stochastic.pt")["ddim_eta"]
+    model, _ = get_model(pkg, "dm1")
+    model.set_precision("fp32")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    img = gd.ddim_sample(model, 32, batch_size=2, channels=3, ddim_timesteps=g["n"], ddim_eta=g["eta"],
+                         x_T=g["x_T"], noise=list(g["noise"]))
+    err = float(np.abs(img - g["final"].numpy()).max())
+    print(f"DDIM eta={g['eta']} final max|err| = {err:.3e}")
+    assert err <= TOL_FP32
+    model.set_precision("bf16")
+    model.release_engines()
+
+
+def test_attack_loop_single_rank(pkg):
+    """Sampler -> composite -> PyTorch victim -> success flags, K=2 candidates per image (world size 1)."""
+    from advshadow_b200.attack import AttackLoop
+    from advshadow_b200.sampler import ShadowSampler
+    model, _ = get_model(pkg, "dm1")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    B_img, K, S = 3, 2, 32
+    sampler = ShadowSampler(model, gd, B_img * K, S, ddim_timesteps=4)
+    torch.manual_seed(0)
+    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                                 torch.nn.Linear(8, 37)).cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    x_T = torch.randn(B_img * K, 3, S, S, generator=g)
+    clean = torch.rand(B_img, 3, S, S, generator=g).repeat_interleave(K, 0)
+    fmask = torch.ones(B_img * K, 1, S, S)
+    centers = torch.full((B_img * K, 2), S / 2.0)
+    radii = torch.tensor([6.0, 12.0] * B_img)
+    labels = torch.randint(0, 37, (B_img,), generator=g).repeat_interleave(K, 0)
+    loop = AttackLoop(sampler, victim, candidates=K, victim_size=S)
+    res = loop.step(x_T, clean, fmask, centers, radii, labels)
+    with torch.no_grad():
+        ref = (victim(res["shadowed"]).argmax(1).cpu() != labels).view(B_img, K).any(1)
+    assert torch.equal(res["flags"].bool().cpu(), ref)
+    assert res["total"] == B_img and res["successes"] == int(ref.sum())
+    # the composite only touches the disk: outside it the clean image is returned untouched
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    outside = ((xx - S / 2) ** 2 + (yy - S / 2) ** 2).sqrt() > 12.0
+    assert torch.equal(res["shadowed"].cpu()[:, :, outside], clean[:, :, outside])
+    model.release_engines()
