@@ -41,6 +41,13 @@ constexpr int kBQ = 128;   // queries per CTA
 constexpr int kBK = 128;   // keys per block
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLazyThreshold = 8.0f;  // rescale O only if the row max grew by > 2^8
+// (ex2.approx.ftz.bf16x2 was tried to halve the MUFU load: ptxas splits it into two MUFU.EX2.BF16 ops on
+//  sm_100a, so it buys nothing and costs accuracy -- scores keep the fp32 ex2.)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int DH>
 struct AttnCfg {
@@ -209,7 +216,7 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < kBK; ++i) {
-        s[i] = exp2f(fmaf(s[i], kLog2e, -m_used));
+        s[i] = fast_exp2(fmaf(s[i], kLog2e, -m_used));
         sum += s[i];
       }
       l = fmaf(l, alpha, sum);
