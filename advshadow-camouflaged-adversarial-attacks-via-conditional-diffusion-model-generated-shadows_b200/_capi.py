@@ -34,6 +34,7 @@ class ConvParams(C.Structure):
         ("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p),
         ("heads", C.c_int32), ("qk_scale", C.c_float),
         ("dtype", C.c_int32), ("cout_valid", C.c_int32),
+        ("stats_partial", C.c_void_p),
     ]
 
 
@@ -51,6 +52,10 @@ SIGNATURES = {
     "advs_conv3x3_head": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "advs_groupnorm_workspace_bytes": (_sz, [_i, _i, _i]),
     "advs_groupnorm_stats": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "advs_groupnorm_partial_parts": (C.c_int, [_i, _i]),
+    "advs_groupnorm_partial": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "advs_groupnorm_finalize": (C.c_int, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "advs_conv_sm100_stats_parts": (C.c_int, [_i, _i, _i]),
     "advs_groupnorm_apply": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "advs_conv_simt": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_plan": (C.c_int, [C.POINTER(ConvParams), _vp]),

@@ -236,6 +236,7 @@ extern "C" {
 int advs_conv_simt(const advs_conv_params* p, void* stream) {
   int rc = validate_conv(p, "conv_simt");
   if (rc) return rc;
+  ADVS_CHECK_ARG(p->stats_partial == nullptr, "conv_simt: stats_partial is only produced by the sm100 kernel");
   SimtConvArgs a;
   a.B = p->B; a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.stride = p->stride; a.nseg = p->nseg;
   for (int s = 0; s < 3; ++s) {

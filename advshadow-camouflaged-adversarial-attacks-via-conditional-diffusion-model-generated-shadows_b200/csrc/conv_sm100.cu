@@ -8,141 +8,19 @@
 // * stride-2 convolutions read four "parity" views of the input (even/odd rows x even/odd columns);
 // * ResidualBlock's 1x1 shortcut conv (and the two halves of a virtual concat) are extra K-segments
 //   accumulated into the same TMEM tile;
-// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-5 = epilogue (TMEM -> registers ->
-//   bias / time-embedding / residual -> bf16 -> global).  TMEM holds two accumulator tiles so the
+// * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warps 2-9 = epilogue (TMEM -> registers ->
+//   bias / time-embedding / residual -> bf16 -> global, + optional per-channel GroupNorm partial sums).  TMEM holds two accumulator tiles so the
 //   epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Reference ops replaced: nn.Conv2d at dm1:73, 86, 90, 114-115, 134, 148 (+ the adds at dm1:101,103,127).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 #include "sm100.cuh"
+#include "conv_sm100_common.cuh"
 
 namespace advs {
-
-using namespace sm100;
-
-struct ConvMaps {
-  CUtensorMap a[6];  // [0..3] segment 0 (stride 1: only [0]; stride 2: parity hp*2+wp), [4],[5] segments 1,2
-  CUtensorMap b[3];
-};
-
-struct ConvArgs {
-  int B, H, W, Cout;
-  int tw, th, tn;
-  int tiles_w, tiles_h, tiles_n, m_tiles, n_tiles;
-  int stride, nseg;
-  int taps[3], cblks[3];
-  int total_kb;
-  uint32_t a_bytes;
-  EpilogueParams epi;
-};
-
-struct ConvPlan {
-  ConvMaps maps;
-  ConvArgs args;
-  int bn;
-  int grid;
-  uint32_t smem_bytes;
-  uint32_t magic;
-};
-static_assert(sizeof(ConvPlan) <= ADVS_CONV_PLAN_BYTES, "ConvPlan does not fit ADVS_CONV_PLAN_BYTES");
-
-constexpr int kConvThreads = 192;
-constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 64 bf16
-
-template <int BN>
-struct ConvCfg {
-  static constexpr uint32_t b_bytes = BN * 128;
-  static constexpr uint32_t stage_bytes = kABytes + b_bytes;
-  static constexpr int stages = (BN == 256) ? 4 : 6;
-  static constexpr uint32_t bar_bytes = 256;
-  static constexpr uint32_t smem_bytes = stages * stage_bytes + bar_bytes + 1024;  // + alignment slack
-  static constexpr uint32_t tmem_cols = 2 * BN;
-};
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-// 32 consecutive output channels [n, n+32) of one pixel row
-__device__ __forceinline__ void epilogue_store32(const EpilogueParams& e, const uint32_t* acc, size_t m, int b, int t,
-                                                 int n) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (e.bias) {
-    const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 t4 = __ldg(bp + j);
-      v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
-    }
-  }
-  if (e.temb) {
-    const float4* tp = reinterpret_cast<const float4*>(e.temb + (size_t)b * e.temb_stride + n);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 t4 = __ldg(tp + j);
-      v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
-    }
-  }
-  if (e.out_mode == 0) {
-    if (e.residual) {
-      const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.Cout + n);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 r4 = __ldg(rp + j);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float2 f = __bfloat1622float2(h[i]);
-          v[8 * j + 2 * i] += f.x;
-          v[8 * j + 2 * i + 1] += f.y;
-        }
-      }
-    }
-    uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 o;
-      o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-      o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-      o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-      yp[j] = o;
-    }
-  } else if (e.out_mode == 2) {
-    float* dst = reinterpret_cast<float*>(e.y) + ((size_t)b * e.cout_valid + n) * e.HW + t;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < e.cout_valid) dst[(size_t)j * e.HW] = v[j];
-  } else {
-    const int head = n / (3 * e.dh);
-    const int r = n - head * 3 * e.dh;
-    const int which = r / e.dh;
-    const int d0 = r - which * e.dh;
-    const size_t bh = (size_t)b * e.heads + head;
-    if (which < 2) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh + d0;
-      uint4* yp = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * j] * e.qk_scale, v[8 * j + 1] * e.qk_scale);
-        o.y = pack_bf16x2(v[8 * j + 2] * e.qk_scale, v[8 * j + 3] * e.qk_scale);
-        o.z = pack_bf16x2(v[8 * j + 4] * e.qk_scale, v[8 * j + 5] * e.qk_scale);
-        o.w = pack_bf16x2(v[8 * j + 6] * e.qk_scale, v[8 * j + 7] * e.qk_scale);
-        yp[j] = o;
-      }
-    } else {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh + d0) * e.HW + t;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dst[(size_t)j * e.HW] = __float2bfloat16_rn(v[j]);
-    }
-  }
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -156,6 +34,7 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float2* stat_smem = reinterpret_cast<float2*>(smem + STAGES * Cfg::stage_bytes + Cfg::bar_bytes);  // [2][4][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -170,7 +49,7 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], 8);
     }
     fence_mbar_init();
   }
@@ -251,8 +130,10 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
+    // two warps per TMEM lane quarter: warps 2-5 take the first half of the tile's columns, 6-9 the second
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int col_half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int rows_valid = a.tw * a.th * a.tn;
     int acc = 0;
@@ -272,18 +153,50 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const bool want_stats = a.stats != nullptr;
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = col_half * (BN / 64); chunk < (col_half + 1) * (BN / 64); ++chunk) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + chunk * 32, r);
         tmem_wait_ld();
         const int n = n_tile * BN + chunk * 32;
         if (n >= a.epi.cout_valid) break;   // zero-padded output channels (uniform across the warp)
-        if (valid) epilogue_store32(a.epi, r, m, b, t, n);
+        float v[32];
+        if (valid) {
+          epilogue_compute32(a.epi, r, v, m, b, n);
+          epilogue_write32(a.epi, v, m, b, t, n);
+        }
+        if (want_stats) {
+          // GroupNorm statistics of the tensor just written, per channel (taken before the bf16 rounding:
+          // the rounding error is zero-mean and ~1e-6 of the variance)
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = valid ? v[j] : 0.f;
+            v[j] = x;
+            sq[j] = x * x;
+          }
+          const float cs = warp_column_sums(v, lane);
+          const float cq = warp_column_sums(sq, lane);
+          stat_smem[(acc * 4 + q) * BN + chunk * 32 + lane] = make_float2(cs, cq);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (want_stats) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+        const int e = (warp - 2) * 32 + lane;
+        for (int c = e; c < BN; c += 256) {
+          const int n = n_tile * BN + c;
+          if (n < a.Cout) {
+            float2 t0 = stat_smem[(acc * 4 + 0) * BN + c], t1 = stat_smem[(acc * 4 + 1) * BN + c];
+            float2 t2 = stat_smem[(acc * 4 + 2) * BN + c], t3 = stat_smem[(acc * 4 + 3) * BN + c];
+            reinterpret_cast<float2*>(a.stats)[(size_t)m_tile * a.Cout + n] =
+                make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
+          }
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -292,6 +205,9 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::tmem_cols>(tmem_base);
 }
+
+uint32_t conv_2cta_smem_bytes(int bn);
+int launch_conv_2cta(const ConvPlan* plan, cudaStream_t st);
 
 // ---- host ------------------------------------------------------------------------------------
 PFN_encodeTiled get_encode_tiled() {
@@ -358,6 +274,14 @@ using namespace advs;
 
 extern "C" {
 
+int advs_conv_sm100_stats_parts(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  int tw = largest_divisor_leq(W, 128);
+  int th = largest_divisor_leq(H, 128 / tw);
+  if (th == H && tw == W && 128 / (tw * th) > 1 && B > 1) return 0;   // a tile would span images
+  return (W / tw) * (H / th);
+}
+
 int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   int rc = validate_conv(p, "conv_sm100_plan");
   if (rc) return rc;
@@ -399,11 +323,20 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
     a.total_kb += a.taps[s] * a.cblks[s];
   }
   a.epi = make_epilogue(*p);
+  a.stats = p->stats_partial;
+  if (a.stats) {
+    ADVS_CHECK_ARG(p->out_mode == 0, "conv_sm100_plan: stats_partial needs out_mode 0");
+    ADVS_CHECK_ARG(a.tn == 1, "conv_sm100_plan: stats_partial needs tiles that do not span images (H*W >= 128)");
+  }
 
   int bn = 128;
   if (p->Cout % 256 == 0 && (long long)a.m_tiles * (p->Cout / 256) >= num_sms()) bn = 256;
   plan->bn = bn;
   a.n_tiles = (p->Cout + bn - 1) / bn;
+  // CTA-pair kernel unless disabled (ADVS_CONV_2CTA=0) or there is only one pixel tile
+  static const int env_2cta = [] { const char* e = getenv("ADVS_CONV_2CTA"); return e ? atoi(e) : 1; }();
+  const int two_cta = (env_2cta && a.m_tiles >= 2) ? 1 : 0;
+  plan->two_cta = two_cta;
 
   // ---- TMA descriptors ----
   const uint32_t abox[4] = {64u, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)a.tn};
@@ -428,7 +361,7 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
     }
     uint64_t wd[3] = {(uint64_t)C, (uint64_t)p->seg[s].taps, (uint64_t)p->Cout};
     uint64_t ws[3] = {2, (uint64_t)C * 2, (uint64_t)p->seg[s].taps * C * 2};
-    const uint32_t wbox[3] = {64u, 1u, (uint32_t)bn};
+    const uint32_t wbox[3] = {64u, 1u, (uint32_t)(two_cta ? bn / 2 : bn)};   // CTA pair: each CTA loads half the rows
     rc = encode_bf16_map(&plan->maps.b[s], p->seg[s].w, 3, wd, ws, wbox, "conv_sm100_plan(W)");
     if (rc) return rc;
   }
@@ -440,8 +373,14 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   for (int i = p->nseg; i < 3; ++i) plan->maps.b[i] = plan->maps.b[0];
 
   const int total_tiles = a.m_tiles * a.n_tiles;
-  plan->grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  plan->smem_bytes = bn == 256 ? ConvCfg<256>::smem_bytes : ConvCfg<128>::smem_bytes;
+  if (two_cta) {
+    const int items = ((a.m_tiles + 1) / 2) * a.n_tiles, max_pairs = num_sms() / 2;
+    plan->grid = 2 * (items < max_pairs ? items : max_pairs);
+    plan->smem_bytes = conv_2cta_smem_bytes(bn);
+  } else {
+    plan->grid = total_tiles < num_sms() ? total_tiles : num_sms();
+    plan->smem_bytes = bn == 256 ? ConvCfg<256>::smem_bytes : ConvCfg<128>::smem_bytes;
+  }
   plan->magic = 0xC0A7B200u;
   return ADVS_OK;
 }
@@ -462,6 +401,7 @@ int advs_conv_sm100_launch(const void* plan_host, void* stream) {
     }
     attr_done = true;
   }
+  if (plan->two_cta) return launch_conv_2cta(plan, (cudaStream_t)stream);
   if (plan->bn == 256)
     k_conv_sm100<256><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);
   else

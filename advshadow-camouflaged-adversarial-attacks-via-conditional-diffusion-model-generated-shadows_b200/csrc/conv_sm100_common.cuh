@@ -1,0 +1,154 @@
+// Shared pieces of the tcgen05 implicit-GEMM convolution kernels (1-CTA and 2-CTA variants).
+#pragma once
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace advs {
+
+using namespace sm100;
+
+struct ConvMaps {
+  CUtensorMap a[6];  // [0..3] segment 0 (stride 1: only [0]; stride 2: parity hp*2+wp), [4],[5] segments 1,2
+  CUtensorMap b[3];
+};
+
+struct ConvArgs {
+  int B, H, W, Cout;
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_n, m_tiles, n_tiles;
+  int stride, nseg;
+  int taps[3], cblks[3];
+  int total_kb;
+  uint32_t a_bytes;
+  float* stats;   // optional [m_tiles][Cout][2] per-tile channel sums / sums of squares (GroupNorm fusion)
+  EpilogueParams epi;
+};
+
+struct ConvPlan {
+  ConvMaps maps;
+  ConvArgs args;
+  int bn;
+  int grid;
+  uint32_t smem_bytes;
+  uint32_t magic;
+  int two_cta;   // 1: CTA-pair kernel (cta_group::2), grid is a multiple of 2
+};
+static_assert(sizeof(ConvPlan) <= ADVS_CONV_PLAN_BYTES, "ConvPlan does not fit ADVS_CONV_PLAN_BYTES");
+
+constexpr int kConvThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr uint32_t kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+template <int BN>
+struct ConvCfg {
+  static constexpr uint32_t b_bytes = BN * 128;
+  static constexpr uint32_t stage_bytes = kABytes + b_bytes;
+  static constexpr int stages = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t bar_bytes = 256;
+  static constexpr uint32_t stat_bytes = 2 * 4 * BN * 8;   // [2 accumulators][4 warps][BN] float2
+  static constexpr uint32_t smem_bytes = stages * stage_bytes + bar_bytes + stat_bytes + 1024;  // + alignment slack
+  static constexpr uint32_t tmem_cols = 2 * BN;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 32 consecutive output channels [n, n+32) of one pixel row: v = acc + bias + temb + residual
+__device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, const uint32_t* acc, float* v, size_t m,
+                                                   int b, int n) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (e.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t4 = __ldg(bp + j);
+      v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+    }
+  }
+  if (e.temb) {
+    const float4* tp = reinterpret_cast<const float4*>(e.temb + (size_t)b * e.temb_stride + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 t4 = __ldg(tp + j);
+      v[4 * j] += t4.x; v[4 * j + 1] += t4.y; v[4 * j + 2] += t4.z; v[4 * j + 3] += t4.w;
+    }
+  }
+  if (e.out_mode == 0 && e.residual) {
+    const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.Cout + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 r4 = __ldg(rp + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[8 * j + 2 * i] += f.x;
+        v[8 * j + 2 * i + 1] += f.y;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_write32(const EpilogueParams& e, const float* v, size_t m, int b, int t, int n) {
+  if (e.out_mode == 0) {
+    uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
+      o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+      o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+      yp[j] = o;
+    }
+  } else if (e.out_mode == 2) {
+    float* dst = reinterpret_cast<float*>(e.y) + ((size_t)b * e.cout_valid + n) * e.HW + t;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < e.cout_valid) dst[(size_t)j * e.HW] = v[j];
+  } else {
+    const int head = n / (3 * e.dh);
+    const int r = n - head * 3 * e.dh;
+    const int which = r / e.dh;
+    const int d0 = r - which * e.dh;
+    const size_t bh = (size_t)b * e.heads + head;
+    if (which < 2) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh + d0;
+      uint4* yp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * j] * e.qk_scale, v[8 * j + 1] * e.qk_scale);
+        o.y = pack_bf16x2(v[8 * j + 2] * e.qk_scale, v[8 * j + 3] * e.qk_scale);
+        o.z = pack_bf16x2(v[8 * j + 4] * e.qk_scale, v[8 * j + 5] * e.qk_scale);
+        o.w = pack_bf16x2(v[8 * j + 6] * e.qk_scale, v[8 * j + 7] * e.qk_scale);
+        yp[j] = o;
+      }
+    } else {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh + d0) * e.HW + t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[(size_t)j * e.HW] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+// Column sums over the 32 rows held by a warp: v[i] of lane l = value (row l, column i).  After the five
+// exchange rounds lane l holds the sum of column l (31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_column_sums(float* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = upper ? v[i + s] : v[i];
+      const float send = upper ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+
+}  // namespace advs

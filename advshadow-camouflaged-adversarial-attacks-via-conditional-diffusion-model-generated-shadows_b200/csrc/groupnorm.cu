@@ -102,22 +102,29 @@ __global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot
   }
 }
 
-// one warp per (image, group)
-__global__ void k_gn_finalize(const float* __restrict__ part, int chunks, int Ctot, int groups, int HW, float eps,
-                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                              float* __restrict__ scale_shift, int B) {
+// one warp per (image, group); the group's channels may straddle the two concatenated sources.
+// part_s layout: [B][parts_s][C_s][2]
+__global__ void k_gn_finalize(const float* __restrict__ part0, int c0, int parts0, const float* __restrict__ part1,
+                              int c1, int parts1, int groups, int HW, float eps, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ scale_shift, int B) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= B * groups) return;
+  const int Ctot = c0 + c1;
   int b = warp / groups, g = warp % groups;
   int cpg = Ctot / groups;
   double S = 0.0, SS = 0.0;
-  int n_items = chunks * cpg;
-  for (int it = lane; it < n_items; it += 32) {
-    int ch = it / cpg, c = g * cpg + it % cpg;
-    const float* p = part + (((size_t)b * chunks + ch) * Ctot + c) * 2;
-    S += (double)p[0];
-    SS += (double)p[1];
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = g * cpg + cc;
+    const float* base;
+    int parts, C, cl;
+    if (c < c0) { base = part0; parts = parts0; C = c0; cl = c; }
+    else { base = part1; parts = parts1; C = c1; cl = c - c0; }
+    for (int p = lane; p < parts; p += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(base + (((size_t)b * parts + p) * C + cl) * 2);
+      S += (double)v.x;
+      SS += (double)v.y;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -199,31 +206,42 @@ __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict
 }
 
 template <typename T>
+static int gn_partial_impl(const void* x, int C, int B, int HW, float* part, cudaStream_t st) {
+  GnGeom g = gn_geom(B, HW);
+  int cv = C / 8;
+  int threads = cv <= 256 ? 256 : 1024;
+  int ppi = threads / cv;
+  size_t smem = (size_t)ppi * C * sizeof(float);
+  dim3 grid(g.chunks, B);
+  k_gn_partial<T><<<grid, threads, smem, st>>>((const T*)x, C, 0, C, HW, g.pix_per_chunk, part);
+  ADVS_CHECK_LAUNCH("groupnorm_partial");
+  return ADVS_OK;
+}
+
+static int gn_finalize_impl(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1, int B,
+                            int HW, int groups, float eps, const float* gamma, const float* beta, float* scale_shift,
+                            cudaStream_t st) {
+  int warps = B * groups;
+  k_gn_finalize<<<(warps * 32 + 127) / 128, 128, 0, st>>>(part0, c0, parts0, part1, c1, parts1, groups, HW, eps, gamma,
+                                                         beta, scale_shift, B);
+  ADVS_CHECK_LAUNCH("groupnorm_finalize");
+  return ADVS_OK;
+}
+
+template <typename T>
 static int gn_stats_impl(const void* x0, int c0, const void* x1, int c1, int B, int HW, int groups, float eps,
                          const float* gamma, const float* beta, float* scale_shift, void* ws, cudaStream_t st) {
   GnGeom g = gn_geom(B, HW);
-  int Ctot = c0 + c1;
-  float* part = (float*)ws;
-  const void* xs[2] = {x0, x1};
-  int cs[2] = {c0, c1};
-  int off = 0;
-  for (int s = 0; s < 2; ++s) {
-    int C = cs[s];
-    if (C == 0) continue;
-    int cv = C / 8;
-    int threads = cv <= 256 ? 256 : 1024;
-    int ppi = threads / cv;
-    size_t smem = (size_t)ppi * C * sizeof(float);
-    dim3 grid(g.chunks, B);
-    k_gn_partial<T><<<grid, threads, smem, st>>>((const T*)xs[s], C, off, Ctot, HW, g.pix_per_chunk, part);
-    ADVS_CHECK_LAUNCH("groupnorm_stats/partial");
-    off += C;
+  float* p0 = (float*)ws;
+  float* p1 = p0 + (size_t)B * g.chunks * c0 * 2;
+  int rc = gn_partial_impl<T>(x0, c0, B, HW, p0, st);
+  if (rc) return rc;
+  if (c1) {
+    rc = gn_partial_impl<T>(x1, c1, B, HW, p1, st);
+    if (rc) return rc;
   }
-  int warps = B * groups;
-  k_gn_finalize<<<(warps * 32 + 127) / 128, 128, 0, st>>>(part, g.chunks, Ctot, groups, HW, eps, gamma, beta,
-                                                         scale_shift, B);
-  ADVS_CHECK_LAUNCH("groupnorm_stats/finalize");
-  return ADVS_OK;
+  return gn_finalize_impl(p0, c0, g.chunks, c1 ? p1 : nullptr, c1, c1 ? g.chunks : 0, B, HW, groups, eps, gamma, beta,
+                          scale_shift, st);
 }
 
 template <typename T>
@@ -268,6 +286,30 @@ int advs_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int B, 
   if (dtype == ADVS_BF16)
     return gn_stats_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, groups, eps, gamma, beta, scale_shift, workspace, (cudaStream_t)stream);
   ADVS_CHECK_ARG(false, "groupnorm_stats: bad dtype");
+}
+
+int advs_groupnorm_partial_parts(int B, int HW) {
+  if (B <= 0 || HW <= 0) return 0;
+  return gn_geom(B, HW).chunks;
+}
+
+int advs_groupnorm_partial(const void* x, int C, int B, int HW, float* part, int dtype, void* stream) {
+  ADVS_CHECK_ARG(x && part && C > 0 && C % 8 == 0 && C / 8 <= 1024 && B > 0 && HW > 0, "groupnorm_partial: bad args");
+  if (dtype == ADVS_F32) return gn_partial_impl<float>(x, C, B, HW, part, (cudaStream_t)stream);
+  if (dtype == ADVS_BF16) return gn_partial_impl<__nv_bfloat16>(x, C, B, HW, part, (cudaStream_t)stream);
+  ADVS_CHECK_ARG(false, "groupnorm_partial: bad dtype");
+}
+
+int advs_groupnorm_finalize(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1, int B,
+                            int HW, int groups, float eps, const float* gamma, const float* beta, float* scale_shift,
+                            void* stream) {
+  ADVS_CHECK_ARG(part0 && c0 > 0 && parts0 > 0 && B > 0 && HW > 0 && groups > 0, "groupnorm_finalize: bad args");
+  if (!part1) { c1 = 0; parts1 = 0; }
+  ADVS_CHECK_ARG(c1 == 0 || parts1 > 0, "groupnorm_finalize: second source has no partial rows");
+  ADVS_CHECK_ARG((c0 + c1) % groups == 0, "groupnorm_finalize: channels not divisible by groups");
+  ADVS_CHECK_ARG(gamma && beta && scale_shift, "groupnorm_finalize: null pointer");
+  return gn_finalize_impl(part0, c0, parts0, part1, c1, parts1, B, HW, groups, eps, gamma, beta, scale_shift,
+                          (cudaStream_t)stream);
 }
 
 int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* scale_shift,

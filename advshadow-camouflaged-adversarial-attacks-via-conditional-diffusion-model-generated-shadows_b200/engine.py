@@ -26,7 +26,7 @@ class UNetEngine:
     """One (spec, batch, height, width, precision) instance of the denoiser on one GPU."""
 
     def __init__(self, spec: UNetSpec, params: Dict[str, torch.Tensor], B: int, H: int, W: int,
-                 precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto"):
+                 precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto", fuse_gn_stats: bool = True):
         if precision not in _DT:
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         any_p = next(iter(params.values()))
@@ -56,6 +56,22 @@ class UNetEngine:
             if b.shape and b.shape[0] == "gn_ws":
                 _, bb, hw, c = b.shape
                 b.elems = int(self.lib.advs_groupnorm_workspace_bytes(bb, hw, c)) // 4
+        # GroupNorm statistics for free: a tcgen05 conv can emit per-tile channel sums of the tensor it
+        # writes; attach such a partial buffer (same lifetime as the tensor) to every conv output a
+        # GroupNorm will read
+        self._stat_buf = {}
+        gn_inputs = {s for op in plan.ops if op.kind == "gn" for s in op.args["srcs"]}
+        if fuse_gn_stats:
+            for idx, op in enumerate(plan.ops):
+                a = op.args
+                if op.kind != "conv" or a["qkv"] is not None or a["dst"] not in gn_inputs or not self._conv_sm100_ok(a):
+                    continue
+                parts = int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
+                if parts <= 0:
+                    continue
+                name = plan.new_buf("gnpart", (B, parts, a["cout"], 2), "f32")
+                plan.bufs[name].first, plan.bufs[name].last = idx, plan.bufs[a["dst"]].last
+                self._stat_buf[a["dst"]] = (name, parts)
         plan.assign_offsets(self.act_bytes)
 
         dev = self.device
@@ -210,13 +226,26 @@ class UNetEngine:
                 x0, c0 = self._ptr(srcs[0]), plan.shape(srcs[0])[3]
                 x1, c1 = (self._ptr(srcs[1]), plan.shape(srcs[1])[3]) if len(srcs) > 1 else (None, 0)
                 g, bt = self._gn[a["weight"]]
-                wsb = plan.bufs[a["ws"]]
-                L.append((lib.advs_groupnorm_stats, (x0, c0, x1, c1, B, a["HW"], a["groups"], 1e-5, g.data_ptr(),
-                                                     bt.data_ptr(), self._ptr(a["ss"]), self._ptr(a["ws"]),
-                                                     wsb.elems * 4, dt), "gn_stats"))
+                chunks = int(lib.advs_groupnorm_partial_parts(B, a["HW"]))
+                parts, ws_off = [], 0
+                for sname in srcs:
+                    cs = plan.shape(sname)[3]
+                    if sname in self._stat_buf:          # statistics came out of the producing conv's epilogue
+                        pbuf, np_ = self._stat_buf[sname]
+                        parts.append((self._ptr(pbuf), np_))
+                    else:
+                        ptr = self._ptr(a["ws"]) + ws_off
+                        ws_off += B * chunks * cs * 2 * 4
+                        L.append((lib.advs_groupnorm_partial, (self._ptr(sname), cs, B, a["HW"], ptr, dt), "gn_stats"))
+                        parts.append((ptr, chunks))
+                        self.n_kernels += 1
+                p1, n1 = parts[1] if len(parts) > 1 else (None, 0)
+                L.append((lib.advs_groupnorm_finalize, (parts[0][0], c0, parts[0][1], p1, c1, n1, B, a["HW"], a["groups"],
+                                                        1e-5, g.data_ptr(), bt.data_ptr(), self._ptr(a["ss"])),
+                          "gn_finalize"))
                 L.append((lib.advs_groupnorm_apply, (x0, c0, x1, c1, B, a["HW"], self._ptr(a["ss"]),
                                                      1 if a["silu"] else 0, self._ptr(a["dst"]), dt), "gn_apply"))
-                self.n_kernels += 3 + (1 if len(srcs) > 1 else 0)
+                self.n_kernels += 2
             elif op.kind == "conv":
                 cp = capi.ConvParams()
                 cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], a["cout"], a["stride"], len(a["segs"])
@@ -239,6 +268,8 @@ class UNetEngine:
                     cp.out_mode = 0
                     cp.y = self._ptr(a["dst"])
                 cp.dtype = dt
+                if a["dst"] in self._stat_buf:
+                    cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
                 self._keep.append(cp)
                 if self._conv_sm100_ok(a):
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
@@ -331,7 +362,10 @@ class UNetEngine:
             a = op.args
             if op.kind == "gn":
                 n = self.B * a["HW"] * a["C"]
-                out.append(("gn_stats", 0, n * ab))                  # one read
+                for sname in a["srcs"]:
+                    if sname not in self._stat_buf:
+                        out.append(("gn_stats", 0, self.B * a["HW"] * plan.shape(sname)[3] * ab))   # one read
+                out.append(("gn_finalize", 0, 0))
                 out.append(("gn_apply", 0, 2 * n * ab))              # one read + one write
             elif op.kind == "conv":
                 k = sum(plan.shape(s)[3] * taps for (s, _, taps, _) in a["segs"])

@@ -237,7 +237,8 @@ def main():
         fwd_ms = sum(d["ms"] for d in prof.values())
         breakdown = {k: {"ms": round(d["ms"], 3), "share": round(d["ms"] / fwd_ms, 4),
                          "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1) if d["flops"] else None,
-                         "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1), "launches": round(d["launches"])}
+                         "gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["bytes"] else None,
+                         "launches": round(d["launches"])}
                      for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
         flops_per_img = sampler.eng.plan.flops / B * n
         out = {

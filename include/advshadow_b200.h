@@ -80,6 +80,16 @@ size_t advs_groupnorm_workspace_bytes(int B, int HW, int C);
 int advs_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int B, int HW, int groups,
                          float eps, const float* gamma, const float* beta, float* scale_shift,
                          void* workspace, size_t workspace_bytes, int dtype, void* stream);
+/* The two halves of advs_groupnorm_stats, usable separately:
+ * advs_groupnorm_partial: per-(image, pixel-chunk, channel) {sum, sumsq} of ONE source,
+ *   part[B][advs_groupnorm_partial_parts(B,HW)][C][2];
+ * advs_groupnorm_finalize: combines the partial rows of up to two concatenated sources (from
+ *   advs_groupnorm_partial or from a conv epilogue's stats_partial) into scale_shift[B][c0+c1][2]. */
+int advs_groupnorm_partial_parts(int B, int HW);
+int advs_groupnorm_partial(const void* x, int C, int B, int HW, float* part, int dtype, void* stream);
+int advs_groupnorm_finalize(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1,
+                            int B, int HW, int groups, float eps, const float* gamma, const float* beta,
+                            float* scale_shift, void* stream);
 int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW,
                          const float* scale_shift, int silu, void* y, int dtype, void* stream);
 
@@ -121,6 +131,10 @@ typedef struct advs_conv_params {
   float qk_scale;
   int32_t dtype;
   int32_t cout_valid;     /* out_mode 2: number of real output channels (<= Cout) */
+  /* optional (sm100 path, out_mode 0): per-tile, per-channel {sum, sum of squares} of the stored output,
+   * layout [B][advs_conv_sm100_stats_parts(B,H,W)][Cout][2] fp32 -- the GroupNorm statistics of the
+   * tensor come for free from the conv epilogue (feed to advs_groupnorm_finalize) */
+  float* stats_partial;
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */
@@ -131,6 +145,8 @@ int advs_conv_simt(const advs_conv_params* p, void* stream);
  * re-created when any pointer in `p` changes.  ADVS_CONV_PLAN_BYTES bytes, 64-byte aligned,
  * caller-owned host memory. */
 #define ADVS_CONV_PLAN_BYTES 2048
+/* number of per-image partial rows the conv epilogue writes into stats_partial (0 = unsupported shape) */
+int advs_conv_sm100_stats_parts(int B, int H, int W);
 int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host);
 int advs_conv_sm100_launch(const void* plan_host, void* stream);
 

@@ -237,3 +237,50 @@ def test_head_conv_nchw_f32_output(ops, impl, dtype, tol):
     capi.call("advs_conv3x3_head", x.data_ptr(), w32.data_ptr(), bias.data_ptr(), y2.data_ptr(), B, H, W, cin, cout,
               cp.dtype, st)
     assert rel_err(y2, ref) < tol
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 128, 256), (3, 8, 32, 64, 192), (1, 4, 256, 128, 128)])
+def test_conv_epilogue_groupnorm_statistics(ops, case):
+    """The tcgen05 conv epilogue can emit per-tile channel sums of the tensor it stores; finalised, they
+    must equal the stand-alone GroupNorm statistics kernel run on that tensor (K5 fused into K1)."""
+    import ctypes as C
+    from advshadow_b200 import _capi as capi
+    B, H, W, cin, cout = case
+    torch.manual_seed(10)
+    lib = capi.lib()
+    x = torch.randn(B, H, W, cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / 20).to(torch.bfloat16).float()
+    bias = torch.randn(cout, device="cuda")
+    wp = ops.pack_conv_weight(w, torch.bfloat16)
+    parts = lib.advs_conv_sm100_stats_parts(B, H, W)
+    assert parts > 0
+    part = torch.full((B, parts, cout, 2), float("nan"), device="cuda")
+    y = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device="cuda")
+    cp = capi.ConvParams()
+    cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, cout, 1, 1
+    cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), wp.data_ptr(), cin, 9
+    cp.bias, cp.out_mode, cp.y, cp.dtype, cp.stats_partial = bias.data_ptr(), 0, y.data_ptr(), capi.BF16, part.data_ptr()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+    capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+    capi.call("advs_conv_sm100_launch", pb.ptr, st)
+    # per-channel sums straight from the stored tensor (the epilogue sums the fp32 values before the bf16
+    # rounding: zero-mean differences of relative size 2^-9 per element)
+    yf = y.float()
+    ref_sum = yf.sum(dim=(1, 2))
+    ref_sq = (yf * yf).sum(dim=(1, 2))
+    got = part.sum(dim=1)
+    assert torch.isfinite(part).all()
+    assert (got[..., 0] - ref_sum).abs().max() <= 4e-3 * ref_sq.sqrt().max()
+    assert ((got[..., 1] - ref_sq).abs() / ref_sq).max() < 2e-3
+    # finalised scale/shift == the stand-alone statistics path
+    g, bt = torch.randn(cout, device="cuda"), torch.randn(cout, device="cuda")
+    ss_f = torch.empty(B, cout, 2, device="cuda")
+    capi.call("advs_groupnorm_finalize", part.data_ptr(), cout, parts, None, 0, 0, B, H * W, 32, 1e-5, g.data_ptr(),
+              bt.data_ptr(), ss_f.data_ptr(), st)
+    ss_s = torch.empty(B, cout, 2, device="cuda")
+    wsb = lib.advs_groupnorm_workspace_bytes(B, H * W, cout)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    capi.call("advs_groupnorm_stats", y.data_ptr(), cout, None, 0, B, H * W, 32, 1e-5, g.data_ptr(), bt.data_ptr(),
+              ss_s.data_ptr(), ws.data_ptr(), wsb, capi.BF16, st)
+    assert (ss_f - ss_s).abs().max() <= 2e-3 * ss_s.abs().max()

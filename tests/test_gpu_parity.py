@@ -46,20 +46,24 @@ FORWARD_CASES = [("dm1", "dm1_32", "dm1_checksum"), ("dm1", "dm1_64", "dm1_check
 
 
 @pytest.mark.parametrize("flavour,key,ck", FORWARD_CASES)
-@pytest.mark.parametrize("precision,conv,attn,tol", [("fp32", "simt", "simt", TOL_FP32), ("bf16", "simt", "simt", TOL_BF16),
-                                                     ("bf16", "sm100", "simt", TOL_BF16), ("bf16", "sm100", "sm100", TOL_BF16)])
-def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision, conv, attn, tol):
+@pytest.mark.parametrize("precision,conv,attn,fuse,tol",
+                         [("fp32", "simt", "simt", True, TOL_FP32), ("bf16", "simt", "simt", True, TOL_BF16),
+                          ("bf16", "sm100", "simt", True, TOL_BF16), ("bf16", "sm100", "sm100", False, TOL_BF16),
+                          ("bf16", "sm100", "sm100", True, TOL_BF16)])
+def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision, conv, attn, fuse, tol):
     g = golden("forwards.pt")
     case = g[key]
     model, chk = get_model(pkg, flavour)
     want = g[ck] if ck else case["checksum"]
     assert abs(chk - want) <= 1e-6 * want, "seeded weights differ from the fixture"
     x, t = case["x"].cuda(), case["t"].cuda()
-    eng = model.engine(x.shape[0], x.shape[2], x.shape[3], precision=precision, conv_impl=conv, attn_impl=attn)
+    eng = model.engine(x.shape[0], x.shape[2], x.shape[3], precision=precision, conv_impl=conv, attn_impl=attn,
+                       fuse_gn_stats=fuse)
     eps = eng.forward(x, t)
     torch.cuda.synchronize()
     err = (eps.cpu() - case["eps"]).abs().max().item()
-    print(f"{key} {precision}/{conv}/{attn}: max|eps err| = {err:.3e} (|eps|max {case['eps'].abs().max():.2f})")
+    print(f"{key} {precision}/{conv}/{attn}/fused_gn_stats={fuse}: max|eps err| = {err:.3e} "
+          f"(|eps|max {case['eps'].abs().max():.2f})")
     assert err <= tol
     model.release_engines()
 
