@@ -35,6 +35,7 @@ class ConvParams(C.Structure):
         ("heads", C.c_int32), ("qk_scale", C.c_float),
         ("dtype", C.c_int32), ("cout_valid", C.c_int32),
         ("stats_partial", C.c_void_p),
+        ("up_phase", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -48,6 +49,7 @@ SIGNATURES = {
     "advs_timestep_embedding": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp]),
     "advs_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "advs_pack_conv_weight": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "advs_pack_upconv_weight": (C.c_int, [_vp, _vp, _i, _i, _i, _vp]),
     "advs_conv3x3_stem": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "advs_conv3x3_head": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "advs_groupnorm_workspace_bytes": (_sz, [_i, _i, _i]),

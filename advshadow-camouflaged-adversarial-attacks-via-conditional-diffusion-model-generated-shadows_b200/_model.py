@@ -149,7 +149,8 @@ class UNetModelBase(nn.Module):
     def _weights_token(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def engine(self, B, H, W, precision=None, conv_impl="auto", attn_impl="auto", fuse_gn_stats=True):
+    def engine(self, B, H, W, precision=None, conv_impl="auto", attn_impl="auto", fuse_gn_stats=True,
+               fuse_upsample=True):
         """The (cached) UNetEngine for this input geometry; repacks weights if parameters changed."""
         from .engine import UNetEngine
         precision = precision or self.precision
@@ -161,12 +162,12 @@ class UNetModelBase(nn.Module):
             warnings.warn("UNetModel is in train() mode with dropout>0: the B200 inference path treats "
                           "Dropout as identity (call model.eval(), as main.py:116 does)")
             self._warned_dropout = True
-        key = (B, H, W, precision, conv_impl, attn_impl, fuse_gn_stats, dev.index)
+        key = (B, H, W, precision, conv_impl, attn_impl, fuse_gn_stats, fuse_upsample, dev.index)
         params = dict(self.named_parameters())
         tok = self._weights_token()
         hit = self._engines.get(key)
         if hit is None:
-            eng = UNetEngine(self.spec(), params, B, H, W, precision, conv_impl, attn_impl, fuse_gn_stats)
+            eng = UNetEngine(self.spec(), params, B, H, W, precision, conv_impl, attn_impl, fuse_gn_stats, fuse_upsample)
             self._engines[key] = [eng, tok]
             return eng
         if hit[1] != tok:

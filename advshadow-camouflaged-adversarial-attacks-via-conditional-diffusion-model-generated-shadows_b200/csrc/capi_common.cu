@@ -22,11 +22,16 @@ int validate_conv(const advs_conv_params* p, const char* who) {
   ADVS_CHECK_ARG(p->nseg >= 1 && p->nseg <= 3, "%s: nseg must be 1..3", who);
   for (int s = 0; s < p->nseg; ++s) {
     ADVS_CHECK_ARG(p->seg[s].x && p->seg[s].w, "%s: segment %d has null pointers", who, s);
-    ADVS_CHECK_ARG(p->seg[s].taps == 9 || p->seg[s].taps == 1, "%s: taps must be 9 or 1", who);
+    ADVS_CHECK_ARG(p->seg[s].taps == 9 || p->seg[s].taps == 1 || (s == 0 && p->seg[s].taps == 4),
+                   "%s: taps must be 9, 1 or (segment 0 of an upsample phase) 4", who);
     ADVS_CHECK_ARG(p->seg[s].C > 0 && p->seg[s].C % 4 == 0, "%s: C must be a multiple of 4", who);
     ADVS_CHECK_ARG(s == 0 || p->seg[s].taps == 1, "%s: shortcut segments must be 1x1", who);
   }
   ADVS_CHECK_ARG(p->stride == 1 || p->seg[0].taps == 9, "%s: stride 2 needs a 3x3 kernel", who);
+  ADVS_CHECK_ARG(p->up_phase >= 0 && p->up_phase <= 4, "%s: up_phase must be 0..4", who);
+  ADVS_CHECK_ARG((p->up_phase != 0) == (p->seg[0].taps == 4), "%s: taps = 4 goes with up_phase != 0", who);
+  ADVS_CHECK_ARG(p->up_phase == 0 || (p->stride == 1 && p->out_mode == 0 && p->nseg == 1 && !p->residual),
+                 "%s: an upsample phase is a plain stride-1 NHWC convolution", who);
   ADVS_CHECK_ARG(p->dtype == ADVS_F32 || p->dtype == ADVS_BF16, "%s: bad dtype", who);
   if (p->out_mode == 0) {
     ADVS_CHECK_ARG(p->y != nullptr, "%s: y is null", who);

@@ -237,6 +237,7 @@ int advs_conv_simt(const advs_conv_params* p, void* stream) {
   int rc = validate_conv(p, "conv_simt");
   if (rc) return rc;
   ADVS_CHECK_ARG(p->stats_partial == nullptr, "conv_simt: stats_partial is only produced by the sm100 kernel");
+  ADVS_CHECK_ARG(p->up_phase == 0, "conv_simt: upsample phases are an sm100-kernel feature (use upsample + 3x3 conv)");
   SimtConvArgs a;
   a.B = p->B; a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.stride = p->stride; a.nseg = p->nseg;
   for (int s = 0; s < 3; ++s) {

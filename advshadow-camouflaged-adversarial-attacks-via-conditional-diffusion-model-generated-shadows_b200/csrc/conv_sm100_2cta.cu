@@ -103,6 +103,10 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
                 ch += dy - 1;
                 cw += dx - 1;
               }
+            } else if (taps == 4) {   // 2x2 phase of an upsample-conv on the low-res input
+              amap = &maps.a[0];
+              ch += (tap >> 1) - 1 + a.up_a;
+              cw += (tap & 1) - 1 + a.up_b;
             } else {
               amap = &maps.a[s == 0 ? 0 : 3 + s];
             }
@@ -166,7 +170,7 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       const int dh = rem / a.tw, dw = rem - dh * a.tw;
       const int b = n0 + dn;
       const bool valid = row < rows_valid && b < a.B && m_tile < a.m_tiles;
-      const int t = (h0 + dh) * a.W + (w0 + dw);
+      const int t = a.up ? (2 * (h0 + dh) + a.up_a) * (2 * a.W) + 2 * (w0 + dw) + a.up_b : (h0 + dh) * a.W + (w0 + dw);
       const size_t m = (size_t)b * a.epi.HW + t;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -209,7 +213,7 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
             if (n < a.Cout) {
               float2 t0 = stat_smem[(acc * 4 + 0) * BN + c], t1 = stat_smem[(acc * 4 + 1) * BN + c];
               float2 t2 = stat_smem[(acc * 4 + 2) * BN + c], t3 = stat_smem[(acc * 4 + 3) * BN + c];
-              reinterpret_cast<float2*>(a.stats)[(size_t)m_tile * a.Cout + n] =
+              reinterpret_cast<float2*>(a.stats)[(size_t)((m_tile / a.stats_tpi) * a.stats_rpi + a.stats_off + m_tile % a.stats_tpi) * a.Cout + n] =
                   make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
             }
           }

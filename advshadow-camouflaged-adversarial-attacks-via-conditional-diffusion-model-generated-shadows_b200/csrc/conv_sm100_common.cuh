@@ -20,7 +20,9 @@ struct ConvArgs {
   int taps[3], cblks[3];
   int total_kb;
   uint32_t a_bytes;
-  float* stats;   // optional [m_tiles][Cout][2] per-tile channel sums / sums of squares (GroupNorm fusion)
+  float* stats;   // optional per-tile channel sums / sums of squares (GroupNorm fusion)
+  int stats_tpi, stats_rpi, stats_off;   // row = (m_tile / tpi) * rpi + off + m_tile % tpi
+  int up_a, up_b, up;                    // upsample phase: output pixel (2h+a, 2w+b); up = 0/1
   EpilogueParams epi;
 };
 

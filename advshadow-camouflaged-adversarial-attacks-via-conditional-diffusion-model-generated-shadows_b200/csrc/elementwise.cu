@@ -52,6 +52,29 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ 
   dst[i] = from_f<T>(w[((size_t)o * I + c) * taps + tap]);
 }
 
+// OIHW 3x3 fp32 -> [phase][O][4][I] T (nearest-2x upsample folded into the kernel, see header)
+template <typename T>
+__global__ void k_pack_upconv_weight(const float* __restrict__ w, T* __restrict__ dst, int O, int I) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)4 * O * 4 * I;
+  if (i >= n) return;
+  int c = (int)(i % I);
+  int tap = (int)((i / I) % 4);
+  int o = (int)((i / ((size_t)4 * I)) % O);
+  int phase = (int)(i / ((size_t)4 * I * O));
+  const int a = phase >> 1, b = phase & 1, p = tap >> 1, q = tap & 1;
+  // rows of the 3x3 kernel that land on low-res row offset p for output-row parity a
+  const int r0 = (a == 0) ? (p == 0 ? 0 : 1) : (p == 0 ? 0 : 2);
+  const int r1 = (a == 0) ? (p == 0 ? 0 : 2) : (p == 0 ? 1 : 2);
+  const int c0 = (b == 0) ? (q == 0 ? 0 : 1) : (q == 0 ? 0 : 2);
+  const int c1 = (b == 0) ? (q == 0 ? 0 : 2) : (q == 0 ? 1 : 2);
+  const float* wp = w + ((size_t)o * I + c) * 9;
+  float acc = 0.f;
+  for (int dy = r0; dy <= r1; ++dy)
+    for (int dx = c0; dx <= c1; ++dx) acc += wp[dy * 3 + dx];
+  dst[i] = from_f<T>(acc);
+}
+
 // ---------------------------------------------------------------------------------------
 // stem: x NCHW fp32 (Cin small) -> y NHWC T.  One thread = one pixel x CPT output channels:
 // the 9*Cin inputs sit in registers (coalesced NCHW loads: consecutive lanes = consecutive pixels),
@@ -290,6 +313,20 @@ int advs_pack_conv_weight(const float* w, void* dst, int O, int I, int kh, int k
   else
     ADVS_CHECK_ARG(false, "pack_conv_weight: bad dtype");
   ADVS_CHECK_LAUNCH("pack_conv_weight");
+  return ADVS_OK;
+}
+
+int advs_pack_upconv_weight(const float* w, void* dst, int O, int I, int dtype, void* stream) {
+  ADVS_CHECK_ARG(w && dst && O > 0 && I > 0, "pack_upconv_weight: bad args");
+  size_t n = (size_t)16 * O * I;
+  unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == ADVS_F32)
+    k_pack_upconv_weight<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (float*)dst, O, I);
+  else if (dtype == ADVS_BF16)
+    k_pack_upconv_weight<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, O, I);
+  else
+    ADVS_CHECK_ARG(false, "pack_upconv_weight: bad dtype");
+  ADVS_CHECK_LAUNCH("pack_upconv_weight");
   return ADVS_OK;
 }
 

@@ -26,7 +26,8 @@ class UNetEngine:
     """One (spec, batch, height, width, precision) instance of the denoiser on one GPU."""
 
     def __init__(self, spec: UNetSpec, params: Dict[str, torch.Tensor], B: int, H: int, W: int,
-                 precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto", fuse_gn_stats: bool = True):
+                 precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto", fuse_gn_stats: bool = True,
+                 fuse_upsample: bool = True):
         if precision not in _DT:
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         any_p = next(iter(params.values()))
@@ -48,9 +49,12 @@ class UNetEngine:
             raise ValueError("the tcgen05 kernels are bf16-only; use precision='bf16'")
         self.conv_impl, self.attn_impl = conv_impl, attn_impl
 
-        plan = build_unet_plan(spec, B, H, W, attn_scores_ws=False)
+        # Upsample + conv3x3 as four low-res 2x2 phase convs (tcgen05 path only; fp32 mode keeps the
+        # reference's op order: nearest upsample, then the 3x3 conv)
+        fuse_up = conv_impl == "sm100" and spec.model_channels % 64 == 0 and fuse_upsample
+        plan = build_unet_plan(spec, B, H, W, attn_scores_ws=False, fuse_upsample=fuse_up)
         if any(not self._attn_sm100_ok(op.args) for op in plan.ops if op.kind == "attn"):
-            plan = build_unet_plan(spec, B, H, W, attn_scores_ws=True)
+            plan = build_unet_plan(spec, B, H, W, attn_scores_ws=True, fuse_upsample=fuse_up)
         self.plan: Plan = plan
         for b in plan.bufs.values():
             if b.shape and b.shape[0] == "gn_ws":
@@ -64,10 +68,13 @@ class UNetEngine:
         if fuse_gn_stats:
             for idx, op in enumerate(plan.ops):
                 a = op.args
-                if op.kind != "conv" or a["qkv"] is not None or a["dst"] not in gn_inputs or not self._conv_sm100_ok(a):
+                if op.kind == "upconv":
+                    parts = 4 * int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
+                elif op.kind == "conv" and a["qkv"] is None and self._conv_sm100_ok(a):
+                    parts = int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
+                else:
                     continue
-                parts = int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
-                if parts <= 0:
+                if parts <= 0 or a["dst"] not in gn_inputs:
                     continue
                 name = plan.new_buf("gnpart", (B, parts, a["cout"], 2), "f32")
                 plan.bufs[name].first, plan.bufs[name].last = idx, plan.bufs[a["dst"]].last
@@ -141,6 +148,9 @@ class UNetEngine:
                     self._packed[(wname, sl)] = torch.empty(a["cout"], taps, c, dtype=tdt, device=dev)
                 if a["bias"]:
                     self._bias[tuple(a["bias"])] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
+            elif op.kind == "upconv":
+                self._packed[(a["weight"], "up4")] = torch.empty(4, a["cout"], 4, a["C"], dtype=tdt, device=dev)
+                self._bias[(a["weight"],)] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
         ted = spec.time_embed_dim
         self.temb_w = torch.empty(self.plan.temb_total, ted, dtype=torch.float32, device=dev)
         self.temb_b = torch.empty(self.plan.temb_total, dtype=torch.float32, device=dev)
@@ -162,6 +172,10 @@ class UNetEngine:
         with torch.cuda.device(self.device):
             for (wname, sl), dst in self._packed.items():
                 w = p32(wname + ".weight")
+                if sl == "up4":
+                    capi.call("advs_pack_upconv_weight", w.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1],
+                              capi.BF16 if dst.dtype == torch.bfloat16 else capi.F32, st)
+                    continue
                 if sl is not None:
                     w = w[:, sl[0]:sl[1]].contiguous()
                 O, I, kh, kw = w.shape          # dst may have more (zero) rows than O: the padded head
@@ -295,6 +309,22 @@ class UNetEngine:
                                                         self._ptr(a["dst"]), B, a["heads"], a["T"], a["dh"],
                                                         self._ptr(a["ws"]), wsb.elems * 4, dt), "attn_simt"))
                     self.n_kernels += 3
+            elif op.kind == "upconv":
+                w4, b = self._packed[(a["weight"], "up4")], self._bias[(a["weight"],)]
+                for ph in range(4):
+                    cp = capi.ConvParams()
+                    cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], a["cout"], 1, 1
+                    cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = self._ptr(a["src"]), w4[ph].data_ptr(), a["C"], 4
+                    cp.bias, cp.out_mode, cp.y, cp.dtype, cp.up_phase = b.data_ptr(), 0, self._ptr(a["dst"]), dt, ph + 1
+                    if a["dst"] in self._stat_buf:
+                        cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
+                    self._keep.append(cp)
+                    pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+                    with torch.cuda.device(self.device):
+                        capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+                    self._plans.append(pb)
+                    L.append((lib.advs_conv_sm100_launch, (pb.ptr,), "conv_sm100"))
+                    self.n_kernels += 1
             elif op.kind == "up":
                 L.append((lib.advs_upsample_nearest2x, (self._ptr(a["src"]), self._ptr(a["dst"]), B, a["H"], a["W"],
                                                         a["C"], dt), "upsample"))
@@ -379,6 +409,11 @@ class UNetEngine:
                 c = a["heads"] * a["dh"]
                 name = "attn_sm100" if self._attn_sm100_ok(a) else "attn_simt"
                 out.append((name, 4 * self.B * a["T"] * a["T"] * c, 4 * self.B * a["T"] * c * ab))
+            elif op.kind == "upconv":
+                m = self.B * a["H"] * a["W"]
+                for _ in range(4):     # executed work: 4 taps per output pixel instead of 9
+                    out.append(("conv_sm100", 2 * m * 4 * a["C"] * a["cout"],
+                                (m * a["C"] + 4 * a["C"] * a["cout"] + m * a["cout"]) * ab))
             elif op.kind == "up":
                 n = self.B * a["H"] * a["W"] * a["C"]
                 out.append(("upsample", 0, 5 * n * ab))

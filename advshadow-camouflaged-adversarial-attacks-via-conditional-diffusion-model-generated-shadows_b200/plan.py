@@ -51,7 +51,7 @@ class Buf:
 
 @dataclass
 class Op:
-    kind: str                   # stem | gn | conv | attn | up | head
+    kind: str                   # stem | gn | conv | attn | up | upconv | head
     args: dict = field(default_factory=dict)
 
 
@@ -146,9 +146,12 @@ def _conv_flops(B, H, W, cin, cout, taps):
     return 2 * B * H * W * cin * cout * taps
 
 
-def build_unet_plan(spec: UNetSpec, B: int, H: int, W: int, attn_scores_ws: bool = False) -> Plan:
+def build_unet_plan(spec: UNetSpec, B: int, H: int, W: int, attn_scores_ws: bool = False,
+                    fuse_upsample: bool = False) -> Plan:
     """Op list for eps = UNetModel(x, t).  `attn_scores_ws`: reserve the [B*heads, T, T] fp32 score
-    buffer the SIMT attention needs (the tcgen05 flash kernel needs none)."""
+    buffer the SIMT attention needs (the tcgen05 flash kernel needs none).  `fuse_upsample`: emit
+    Upsample's nearest-2x + conv3x3 (dm1:137-139) as one "upconv" op (four 2x2 phase convolutions on the
+    low-res tensor, 2.25x fewer MACs, no upsampled intermediate) instead of "up" + "conv"."""
     nlev = len(spec.channel_mult)
     if H % (1 << (nlev - 1)) or W % (1 << (nlev - 1)):
         raise ValueError(f"image size {H}x{W} is not divisible by 2^{nlev - 1} (one stride-2 conv per level)")
@@ -270,7 +273,15 @@ def build_unet_plan(spec: UNetSpec, B: int, H: int, W: int, attn_scores_ws: bool
             if ds in spec.attention_resolutions:
                 cur = attn_block(f"up_blocks.{uidx}.{sub}", cur, h, w)
                 sub += 1
-            if level and i == spec.num_res_blocks:
+            if level and i == spec.num_res_blocks and spec.conv_resample and fuse_upsample:
+                dst = p.new_buf("upconv", (B, 2 * h, 2 * w, ch))
+                p.emit("upconv", [cur], [dst], src=cur, dst=dst, weight=f"up_blocks.{uidx}.{sub}.conv", H=h, W=w, C=ch,
+                       cout=ch)
+                p.flops += _conv_flops(B, 2 * h, 2 * w, ch, ch, 9)      # the reference's algorithmic count
+                h, w = 2 * h, 2 * w
+                cur = dst
+                ds //= 2
+            elif level and i == spec.num_res_blocks:
                 up = p.new_buf("up", (B, 2 * h, 2 * w, ch))
                 p.emit("up", [cur], [up], src=cur, dst=up, H=h, W=w, C=ch)
                 h, w = 2 * h, 2 * w

@@ -63,6 +63,11 @@ int advs_linear_f32(const float* x, const float* w, const float* b, float* y, in
 int advs_pack_conv_weight(const float* w_oihw, void* dst, int O, int I, int kh, int kw, int dtype,
                           void* stream);
 
+/* 3x3 weight OIHW fp32 -> four phase kernels [phase = 2a+b][O][2*2][I]: tap (p,q) of phase (a,b) is the sum
+ * of the 3x3 taps that read the same low-res pixel after nearest-2x upsampling
+ * (rows: a=0: {0},{1,2}; a=1: {0,1},{2}; same for columns). */
+int advs_pack_upconv_weight(const float* w_oihw, void* dst, int O, int I, int dtype, void* stream);
+
 /* ---- K1 edge layers: Cin=3 stem and Cout=3 head (dm1:192, dm1:240-242) -------------------- */
 /* x NCHW fp32 [B,Cin,H,W], w fp32 [Cout][9][Cin], y NHWC `dtype` [B,H,W,Cout]. 3x3, pad 1. */
 int advs_conv3x3_stem(const float* x_nchw, const float* w, const float* bias, void* y, int B,
@@ -109,7 +114,7 @@ typedef struct advs_conv_seg {
   const void* x; /* NHWC [B, Hin, Win, C]; Hin = H*stride for segment 0, H otherwise */
   const void* w; /* [Cout][taps][C] in dtype */
   int32_t C;
-  int32_t taps; /* 9 (3x3 pad 1) or 1 (1x1) */
+  int32_t taps; /* 9 (3x3 pad 1), 1 (1x1) or 4 (2x2 phase of an upsample-conv, see up_phase) */
 } advs_conv_seg;
 
 typedef struct advs_conv_params {
@@ -135,6 +140,12 @@ typedef struct advs_conv_params {
    * layout [B][advs_conv_sm100_stats_parts(B,H,W)][Cout][2] fp32 -- the GroupNorm statistics of the
    * tensor come for free from the conv epilogue (feed to advs_groupnorm_finalize) */
   float* stats_partial;
+  /* Upsample(nearest 2x) + conv3x3 (dm1:137-139) as four 2x2 "phase" convolutions on the LOW-RES
+   * input: up_phase = 1 + 2*a + b selects output pixels (2h+a, 2w+b); 0 = ordinary convolution.
+   * With up_phase != 0: B,H,W are the INPUT size, y is [B,2H,2W,Cout], segment 0 has taps = 4 and
+   * weights from advs_pack_upconv_weight; stats_partial rows are [B][4 * parts][Cout][2]. */
+  int32_t up_phase;
+  int32_t reserved;
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */

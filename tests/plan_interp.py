@@ -89,6 +89,10 @@ def run_plan(plan, params, x, timesteps, round_bf16=False):
         elif op.kind == "up":
             y = F.interpolate(_nchw(bufs[a["src"]]), scale_factor=2, mode="nearest")
             bufs[a["dst"]] = _nhwc(y)
+        elif op.kind == "upconv":
+            y = F.interpolate(_nchw(bufs[a["src"]]), scale_factor=2, mode="nearest")
+            y = F.conv2d(y, wr(params[a["weight"] + ".weight"]), params[a["weight"] + ".bias"], padding=1)
+            bufs[a["dst"]] = rnd(_nhwc(y))
         elif op.kind == "head":
             eps = F.conv2d(_nchw(bufs[a["src"]]), params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
         else:

@@ -6,6 +6,6 @@ run parity tests/test_gpu_parity.py -k "forward or config1"
 echo "=== bench"; timeout 1500 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())
-print('value', round(d['value'],3), 'e2e', round(d['e2e']['value'],3), 'conv frac', round(d['roofline']['frac'],3), 'path frac', round(d['whole_path_tensor_frac'],3))
+print('value', round(d['value'],3), 'e2e', round(d['e2e']['value'],3), 'conv frac', round(d['roofline']['frac'],3), 'path frac', round(d['whole_path_tensor_frac'],3), d['clocks'])
 for k, v in d['forward_breakdown'].items(): print(' ', k, v)
 " | tee gpurun_out/bench_quick.log

@@ -284,3 +284,42 @@ def test_conv_epilogue_groupnorm_statistics(ops, case):
     capi.call("advs_groupnorm_stats", y.data_ptr(), cout, None, 0, B, H * W, 32, 1e-5, g.data_ptr(), bt.data_ptr(),
               ss_s.data_ptr(), ws.data_ptr(), wsb, capi.BF16, st)
     assert (ss_f - ss_s).abs().max() <= 2e-3 * ss_s.abs().max()
+
+
+@pytest.mark.parametrize("case", [(2, 8, 16, 128, 128), (1, 32, 32, 64, 192), (1, 2, 128, 64, 64)])
+def test_upsample_conv_as_four_phase_convs(ops, case):
+    """Upsample (dm1:129-140): nearest 2x + conv3x3 == four 2x2 convolutions on the low-res tensor with
+    pre-summed weights (advs_pack_upconv_weight), each writing one parity class of the output pixels;
+    the fused GroupNorm partial statistics cover the whole high-res tensor."""
+    import ctypes as C
+    from advshadow_b200 import _capi as capi
+    B, H, W, cin, cout = case
+    torch.manual_seed(11)
+    lib = capi.lib()
+    x = torch.randn(B, H, W, cin, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / 20).float()
+    bias = torch.randn(cout, device="cuda")
+    w4 = torch.empty(4, cout, 4, cin, dtype=torch.bfloat16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.call("advs_pack_upconv_weight", w.data_ptr(), w4.data_ptr(), cout, cin, capi.BF16, st)
+    y = torch.full((B, 2 * H, 2 * W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    parts = lib.advs_conv_sm100_stats_parts(B, H, W)
+    part = torch.full((B, 4 * parts, cout, 2), float("nan"), device="cuda") if parts else None
+    keep = []
+    for ph in range(4):
+        cp = capi.ConvParams()
+        cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, cout, 1, 1
+        cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), w4[ph].data_ptr(), cin, 4
+        cp.bias, cp.out_mode, cp.y, cp.dtype, cp.up_phase = bias.data_ptr(), 0, y.data_ptr(), capi.BF16, ph + 1
+        if part is not None:
+            cp.stats_partial = part.data_ptr()
+        pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+        capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+        capi.call("advs_conv_sm100_launch", pb.ptr, st)
+        keep.append((cp, pb))
+    ref = F.conv2d(F.interpolate(nchw(x.float()), scale_factor=2, mode="nearest"), w, bias, padding=1)
+    assert rel_err(nchw(y), ref) < 1e-2
+    if part is not None:
+        yf = y.float()
+        assert torch.isfinite(part).all()
+        assert ((part.sum(1)[..., 1] - (yf * yf).sum(dim=(1, 2))).abs() / (yf * yf).sum(dim=(1, 2))).max() < 2e-3

@@ -49,6 +49,7 @@ FORWARD_CASES = [("dm1", "dm1_32", "dm1_checksum"), ("dm1", "dm1_64", "dm1_check
 @pytest.mark.parametrize("precision,conv,attn,fuse,tol",
                          [("fp32", "simt", "simt", True, TOL_FP32), ("bf16", "simt", "simt", True, TOL_BF16),
                           ("bf16", "sm100", "simt", True, TOL_BF16), ("bf16", "sm100", "sm100", False, TOL_BF16),
+                          ("bf16", "sm100", "sm100", "no_upfuse", TOL_BF16),
                           ("bf16", "sm100", "sm100", True, TOL_BF16)])
 def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision, conv, attn, fuse, tol):
     g = golden("forwards.pt")
@@ -58,7 +59,7 @@ def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision
     assert abs(chk - want) <= 1e-6 * want, "seeded weights differ from the fixture"
     x, t = case["x"].cuda(), case["t"].cuda()
     eng = model.engine(x.shape[0], x.shape[2], x.shape[3], precision=precision, conv_impl=conv, attn_impl=attn,
-                       fuse_gn_stats=fuse)
+                       fuse_gn_stats=bool(fuse), fuse_upsample=(fuse != "no_upfuse"))
     eps = eng.forward(x, t)
     torch.cuda.synchronize()
     err = (eps.cpu() - case["eps"]).abs().max().item()
