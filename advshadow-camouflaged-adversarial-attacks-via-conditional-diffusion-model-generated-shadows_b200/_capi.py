@@ -62,6 +62,7 @@ SIGNATURES = {
     "advs_conv_simt": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_plan": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_launch": (C.c_int, [_vp, _vp]),
+    "advs_selftest_umma_row_shift": (C.c_int, [_i, _i, _vp, _vp]),
     "advs_upsample_nearest2x": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "advs_attention_simt_workspace_bytes": (_sz, [_i, _i, _i]),
     "advs_attention_simt": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),

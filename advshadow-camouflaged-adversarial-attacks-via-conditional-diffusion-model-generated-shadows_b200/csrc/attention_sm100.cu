@@ -135,20 +135,26 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp walks the schedule, one elected lane issues) =================
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, kBK);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH);
       const uint32_t q_addr = smem_u32(smem + Cfg::off_q);
       const uint32_t p_addr = smem_u32(smem + Cfg::off_p);
+      // S_j = Q K_j^T, then signal the softmax warps and release the K stage (elected lane only)
       auto issue_s = [&](int j, int st) {
         const uint32_t k_addr = smem_u32(smem + Cfg::off_k + st * Cfg::k_bytes);
         const uint32_t d = tmem_base + (uint32_t)((j & 1) * kBK);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) {
-          const uint32_t off = (uint32_t)(k >> 2) * (128 * 128) + (uint32_t)(k & 3) * 32;
-          umma_bf16(d, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < DH / 16; ++k) {
+            const uint32_t off = (uint32_t)(k >> 2) * (128 * 128) + (uint32_t)(k & 3) * 32;
+            umma_bf16(d, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_s, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[j & 1]);
+          umma_commit(&k_empty[st]);
         }
+        __syncwarp();
       };
       int st = 0;       // stage of block j (the PV side)
       uint32_t ph = 0;
@@ -158,16 +164,12 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_s(0, 0);
-      umma_commit(&s_full[0]);
-      umma_commit(&k_empty[0]);
       if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {
           mbar_wait(&k_full[st_s], ph_s);
           tc_fence_after();
           issue_s(j + 1, st_s);
-          umma_commit(&s_full[(j + 1) & 1]);
-          umma_commit(&k_empty[st_s]);
           if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
         }
         mbar_wait(p_full, (uint32_t)(j & 1));
@@ -175,15 +177,18 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem + Cfg::off_v + st * Cfg::v_bytes);
         const uint32_t d = tmem_base + Cfg::o_col;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint32_t offp = (uint32_t)(k >> 2) * (kBQ * 128) + (uint32_t)(k & 3) * 32;
-          const uint32_t offv = (uint32_t)(k >> 2) * (DH * 128) + (uint32_t)(k & 3) * 32;
-          umma_bf16(d, umma_desc_k_sw128(p_addr + offp), umma_desc_k_sw128(v_addr + offv), idesc_o,
-                    (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint32_t offp = (uint32_t)(k >> 2) * (kBQ * 128) + (uint32_t)(k & 3) * 32;
+            const uint32_t offv = (uint32_t)(k >> 2) * (DH * 128) + (uint32_t)(k & 3) * 32;
+            umma_bf16(d, umma_desc_k_sw128(p_addr + offp), umma_desc_k_sw128(v_addr + offv), idesc_o,
+                      (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(o_done);
+          umma_commit(&v_empty[st]);
         }
-        umma_commit(o_done);
-        umma_commit(&v_empty[st]);
+        __syncwarp();
         if (++st == KVS) { st = 0; ph ^= 1; }
       }
     }

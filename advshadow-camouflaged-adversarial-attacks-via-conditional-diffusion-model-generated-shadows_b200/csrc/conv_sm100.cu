@@ -106,8 +106,8 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp walks the schedule, one elected lane issues) =================
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -123,13 +123,17 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) per 64-channel block
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
+            for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) per 64-channel block
+              umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -212,6 +216,8 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
 
 uint32_t conv_2cta_smem_bytes(int bn);
 int launch_conv_2cta(const ConvPlan* plan, cudaStream_t st);
+uint32_t conv_2cta_halo_smem_bytes(int bn);
+int launch_conv_2cta_halo(const ConvPlan* plan, cudaStream_t st);
 
 // ---- host ------------------------------------------------------------------------------------
 PFN_encodeTiled get_encode_tiled() {
@@ -348,10 +354,24 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   static const int env_2cta = [] { const char* e = getenv("ADVS_CONV_2CTA"); return e ? atoi(e) : 1; }();
   const int two_cta = (env_2cta && a.m_tiles >= 2) ? 1 : 0;
   plan->two_cta = two_cta;
+  // halo reuse: whole 128-pixel row segments, stride 1, a kernel wider than 1x1
+  static const int env_halo = [] { const char* e = getenv("ADVS_CONV_HALO"); return e ? atoi(e) : 1; }();
+  const int halo = (two_cta && env_halo && p->stride == 1 && a.tw == 128 && a.th == 1 && a.tn == 1 &&
+                    (p->seg[0].taps == 9 || p->seg[0].taps == 4)) ? 1 : 0;
+  plan->halo = halo;
+  for (int s = 0; s < 3; ++s) {
+    const int t = a.taps[s];
+    a.a_bytes_seg[s] = (uint32_t)(t == 9 ? 130 * 3 : (t == 4 ? 129 * 2 : 128)) * 128u;
+  }
 
   // ---- TMA descriptors ----
-  const uint32_t abox[4] = {64u, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)a.tn};
+  uint32_t abox[4] = {64u, (uint32_t)a.tw, (uint32_t)a.th, (uint32_t)a.tn};
   for (int s = 0; s < p->nseg; ++s) {
+    if (halo) {
+      const int t = p->seg[s].taps;
+      abox[1] = t == 9 ? 130u : (t == 4 ? 129u : 128u);
+      abox[2] = t == 9 ? 3u : (t == 4 ? 2u : 1u);
+    }
     const int C = p->seg[s].C;
     const char* base = reinterpret_cast<const char*>(p->seg[s].x);
     if (s == 0 && p->stride == 2) {
@@ -387,7 +407,7 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   if (two_cta) {
     const int items = ((a.m_tiles + 1) / 2) * a.n_tiles, max_pairs = num_sms() / 2;
     plan->grid = 2 * (items < max_pairs ? items : max_pairs);
-    plan->smem_bytes = conv_2cta_smem_bytes(bn);
+    plan->smem_bytes = halo ? conv_2cta_halo_smem_bytes(bn) : conv_2cta_smem_bytes(bn);
   } else {
     plan->grid = total_tiles < num_sms() ? total_tiles : num_sms();
     plan->smem_bytes = bn == 256 ? ConvCfg<256>::smem_bytes : ConvCfg<128>::smem_bytes;
@@ -412,6 +432,7 @@ int advs_conv_sm100_launch(const void* plan_host, void* stream) {
     }
     attr_done = true;
   }
+  if (plan->halo) return launch_conv_2cta_halo(plan, (cudaStream_t)stream);
   if (plan->two_cta) return launch_conv_2cta(plan, (cudaStream_t)stream);
   if (plan->bn == 256)
     k_conv_sm100<256><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);

@@ -20,6 +20,7 @@ struct ConvArgs {
   int taps[3], cblks[3];
   int total_kb;
   uint32_t a_bytes;
+  uint32_t a_bytes_seg[3];   // halo kernel: bytes of the activation box of each K-segment
   float* stats;   // optional per-tile channel sums / sums of squares (GroupNorm fusion)
   int stats_tpi, stats_rpi, stats_off;   // row = (m_tile / tpi) * rpi + off + m_tile % tpi
   int up_a, up_b, up;                    // upsample phase: output pixel (2h+a, 2w+b); up = 0/1
@@ -34,6 +35,7 @@ struct ConvPlan {
   uint32_t smem_bytes;
   uint32_t magic;
   int two_cta;   // 1: CTA-pair kernel (cta_group::2), grid is a multiple of 2
+  int halo;      // 1: CTA-pair kernel with one activation halo box per channel block (conv_sm100_halo.cu)
 };
 static_assert(sizeof(ConvPlan) <= ADVS_CONV_PLAN_BYTES, "ConvPlan does not fit ADVS_CONV_PLAN_BYTES");
 

@@ -1,19 +1,12 @@
-// CTA-pair (cta_group::2) variant of the implicit-GEMM convolution.
+// CTA-pair implicit-GEMM convolution with HALO REUSE, for rows of >= 128 pixels (W % 128 == 0, stride 1).
 //
-// Two CTAs of a cluster (the two SMs of a TPC) compute a 256-pixel x BN-cout tile together:
-//   * each CTA TMA-loads ITS OWN 128-pixel activation tile and HALF of the weight tile (BN/2 rows),
-//   * the leader CTA issues tcgen05.mma.cta_group::2 (M = 256): each SM multiplies its 128 rows with
-//     the full BN-row weight tile, whose halves it reads from both CTAs' shared memory,
-//   * each CTA's TMEM holds the accumulator of its own 128 rows and each CTA runs its own epilogue.
-// Per SM and per 64-channel block this moves 16 KB + BN*64 B through TMA and shared memory instead of
-// 16 KB + BN*128 B: the single-CTA kernel is shared-memory-bandwidth bound (TMA writes + UMMA operand reads),
-// worst for Cout = 128 layers (microbench: 797 TFLOP/s vs 1 244 for BN = 256, cuBLAS sustained 1 392).
-//
-// Barrier protocol (every barrier exists at the same offset in both CTAs):
-//   full[s]   leader's copy only: 2 arrivals (leader expect_tx + peer remote arrive) + bytes of both CTAs' TMA
-//   empty[s]  own copy: 1 arrival from the leader's tcgen05.commit multicast
-//   tfull[a]  own copy: 1 arrival from the leader's tcgen05.commit multicast
-//   tempty[a] leader's copy only: 16 arrivals (8 epilogue warps x 2 CTAs)
+// conv_sm100_2cta.cu re-loads the activation tile once per tap (9x for a 3x3 conv) from L2.  Here each
+// (segment, 64-channel block) loads ONE halo box {64 ch, 128 + kx - 1 pixels, ky rows} and every tap reads
+// it through a UMMA descriptor shifted by whole 128-byte rows -- legal because the 128-byte swizzle is a
+// function of the absolute shared-memory address (verified on hardware by advs_selftest_umma_row_shift).
+// L2 -> SM traffic per 64-channel block of a 3x3 conv drops from 9 x 16 KB to 49 KB; the weight tiles
+// stream through their own ring.  Microbench (128->128 3x3 @256^2, batch 64) motivating it: the layer was
+// L2-bandwidth bound at 795 TFLOP/s while BN = 256 layers reach 1 400.
 #include <string.h>
 
 #include "common.cuh"
@@ -23,29 +16,34 @@
 namespace advs {
 
 template <int BN>
-struct ConvCfg2 {
-  static constexpr uint32_t b_bytes = (BN / 2) * 128;          // this CTA's half of the weight tile
-  static constexpr uint32_t stage_bytes = kABytes + b_bytes;
-  static constexpr int stages = (BN == 256) ? 6 : 8;
+struct ConvCfgH {
+  static constexpr uint32_t b_bytes = (BN / 2) * 128;          // this CTA's half of one tap's weight tile
+  static constexpr uint32_t a_buf_bytes = 49 * 1024;           // >= 3 rows x 130 pixels x 128 B, 1 KB aligned
+  static constexpr int a_bufs = 2;
+  static constexpr int stages = (BN == 256) ? 6 : 10;          // weight-tile ring
+  static constexpr uint32_t off_b = a_bufs * a_buf_bytes;
+  static constexpr uint32_t off_bar = off_b + stages * b_bytes;
   static constexpr uint32_t bar_bytes = 512;
   static constexpr uint32_t stat_bytes = 2 * 4 * BN * 8;
-  static constexpr uint32_t smem_bytes = stages * stage_bytes + bar_bytes + stat_bytes + 1024;
+  static constexpr uint32_t smem_bytes = off_bar + bar_bytes + stat_bytes + 1024;
   static constexpr uint32_t tmem_cols = 2 * BN;
 };
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
-k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
-  using Cfg = ConvCfg2<BN>;
+k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
+  using Cfg = ConvCfgH<BN>;
   constexpr int STAGES = Cfg::stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::stage_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar);   // weight ring
   uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* a_full = empty + STAGES;                                   // activation (halo) buffers
+  uint64_t* a_empty = a_full + Cfg::a_bufs;
+  uint64_t* tfull = a_empty + Cfg::a_bufs;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float2* stat_smem = reinterpret_cast<float2*>(smem + STAGES * Cfg::stage_bytes + Cfg::bar_bytes);
+  float2* stat_smem = reinterpret_cast<float2*>(smem + Cfg::off_bar + Cfg::bar_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -61,6 +59,10 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 2);
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::a_bufs; ++s) {
+      mbar_init(&a_full[s], 2);
+      mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -78,8 +80,8 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, abuf = 0;
+      uint32_t phase = 0, aphase = 0;
       for (int item = pair; item < total_items; item += num_pairs) {
         const int m_pair = item / a.n_tiles, n_tile = item - m_pair * a.n_tiles;
         const int m_tile = m_pair * 2 + (int)rank;     // may be == m_tiles for an odd tail: fully out of bounds -> zeros
@@ -89,33 +91,21 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
         const int nb = n_tile * BN + (int)rank * (BN / 2);
         for (int s = 0; s < a.nseg; ++s) {
           const int taps = a.taps[s];
-          for (int tap = 0; tap < taps; ++tap) {
-            const CUtensorMap* amap;
-            int cw = w0, ch = h0;
-            if (taps == 9) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              if (s == 0 && a.stride == 2) {
-                amap = &maps.a[(dy != 1 ? 2 : 0) + (dx != 1 ? 1 : 0)];
-                ch += (dy == 0) ? -1 : 0;
-                cw += (dx == 0) ? -1 : 0;
-              } else {
-                amap = &maps.a[s == 0 ? 0 : 3 + s];
-                ch += dy - 1;
-                cw += dx - 1;
-              }
-            } else if (taps == 4) {   // 2x2 phase of an upsample-conv on the low-res input
-              amap = &maps.a[0];
-              ch += (tap >> 1) - 1 + a.up_a;
-              cw += (tap & 1) - 1 + a.up_b;
-            } else {
-              amap = &maps.a[s == 0 ? 0 : 3 + s];
-            }
-            for (int cb = 0; cb < a.cblks[s]; ++cb) {
+          // one box per (segment, channel block) serves every tap: origin = top-left of the halo
+          int cw = w0, ch = h0;
+          if (taps == 9) { cw -= 1; ch -= 1; }
+          else if (taps == 4) { cw += a.up_b - 1; ch += a.up_a - 1; }
+          const CUtensorMap* amap = &maps.a[s == 0 ? 0 : 3 + s];
+          for (int cb = 0; cb < a.cblks[s]; ++cb) {
+            mbar_wait(&a_empty[abuf], aphase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&a_full[abuf], 2 * a.a_bytes_seg[s]);
+            tma_load_4d_2cta(smem + abuf * Cfg::a_buf_bytes, amap, &a_full[abuf], cb * 64, cw, ch, n0);
+            if (!leader) mbar_arrive_leader(&a_full[abuf]);
+            if (++abuf == Cfg::a_bufs) { abuf = 0; aphase ^= 1; }
+            for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * Cfg::stage_bytes;
-              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (a.a_bytes + Cfg::b_bytes));
-              tma_load_4d_2cta(sa, amap, &full[stage], cb * 64, cw, ch, n0);
-              tma_load_3d_2cta(sa + kABytes, &maps.b[s], &full[stage], cb * 64, tap, nb);
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::b_bytes);
+              tma_load_3d_2cta(smem + Cfg::off_b + stage * Cfg::b_bytes, &maps.b[s], &full[stage], cb * 64, tap, nb);
               if (!leader) mbar_arrive_leader(&full[stage]);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -127,28 +117,42 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader) {   // the whole warp walks the schedule; one elected lane issues (warp-uniform control flow)
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, abuf = 0;
+      uint32_t phase = 0, aphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = pair; item < total_items; item += num_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < a.total_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
-          if (elect_one()) {
+        uint32_t first = 1;
+        for (int s = 0; s < a.nseg; ++s) {
+          const int taps = a.taps[s];
+          for (int cb = 0; cb < a.cblks[s]; ++cb) {
+            mbar_wait(&a_full[abuf], aphase);
+            const uint32_t a_base = smem_u32(smem + abuf * Cfg::a_buf_bytes);
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              // the tap is a whole-row shift inside the halo box; SWIZZLE_128B is a function of the absolute
+              // shared-memory address, so a row-shifted descriptor reads what TMA wrote (selftest_sm100.cu)
+              const int row_off = taps == 9 ? (tap / 3) * 130 + tap % 3 : (taps == 4 ? (tap >> 1) * 129 + (tap & 1) : 0);
+              const uint64_t adesc = umma_desc_k_sw128(a_base + (uint32_t)row_off * 128u);
+              const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem + Cfg::off_b + stage * Cfg::b_bytes));
+              if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_2cta(&empty[stage], 3);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                umma_commit_2cta(&empty[stage], 3);
+              }
+              __syncwarp();
+              first = 0;
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one()) umma_commit_2cta(&a_empty[abuf], 3);
+            __syncwarp();
+            if (++abuf == Cfg::a_bufs) { abuf = 0; aphase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) umma_commit_2cta(&tfull[acc], 3);
         __syncwarp();
@@ -233,26 +237,26 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   if (warp == 1) tmem_dealloc_2cta<Cfg::tmem_cols>(tmem_base);
 }
 
-uint32_t conv_2cta_smem_bytes(int bn) { return bn == 256 ? ConvCfg2<256>::smem_bytes : ConvCfg2<128>::smem_bytes; }
+uint32_t conv_2cta_halo_smem_bytes(int bn) { return bn == 256 ? ConvCfgH<256>::smem_bytes : ConvCfgH<128>::smem_bytes; }
 
-int launch_conv_2cta(const ConvPlan* plan, cudaStream_t st) {
+int launch_conv_2cta_halo(const ConvPlan* plan, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ConvCfg2<128>::smem_bytes);
-    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ConvCfg2<256>::smem_bytes);
+    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ConvCfgH<128>::smem_bytes);
+    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ConvCfgH<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      set_error("conv_sm100_launch(2cta): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      set_error("conv_sm100_launch(halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       return ADVS_ERR_CUDA;
     }
     attr_done = true;
   }
   if (plan->bn == 256)
-    k_conv_sm100_2cta<256><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    k_conv_sm100_2cta_halo<256><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
   else
-    k_conv_sm100_2cta<128><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-  ADVS_CHECK_LAUNCH("conv_sm100_launch(2cta)");
+    k_conv_sm100_2cta_halo<128><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  ADVS_CHECK_LAUNCH("conv_sm100_launch(halo)");
   return ADVS_OK;
 }
 

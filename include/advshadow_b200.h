@@ -161,6 +161,10 @@ int advs_conv_sm100_stats_parts(int B, int H, int W);
 int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host);
 int advs_conv_sm100_launch(const void* plan_host, void* stream);
 
+/* hardware self-test used by the test-suite: D[i][j] = A[r0+i][j] through a row-shifted SWIZZLE_128B UMMA
+ * descriptor (out: fp32 [128][64]); base_offset_mode selects the descriptor's base-offset convention */
+int advs_selftest_umma_row_shift(int r0, int base_offset_mode, float* out, void* stream);
+
 /* ---- K7: nearest 2x upsample (dm1:137) ---------------------------------------------------- */
 int advs_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, int dtype,
                             void* stream);

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name"; timeout 600 python -m pytest "$@" -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -${TAILN:-8} | tee gpurun_out/$name.log; }
-run kernels tests/test_gpu_kernels.py -k "conv"
+run kernels tests/test_gpu_kernels.py -k "conv or attention"
 run parity tests/test_gpu_parity.py -k "forward"
-echo "=== microbench 2cta"; timeout 300 python tools/microbench_conv.py 2>&1 | grep -v attention | tail -12
+echo "=== microbench"; timeout 300 python tools/microbench_conv.py 2>&1 | tail -14
 echo "=== bench"; timeout 1500 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read())

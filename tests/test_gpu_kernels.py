@@ -58,7 +58,9 @@ CONV_CASES = [
     (2, 16, 16, 128, 192, 1, 1),    # 1x1, Cout not a multiple of 128
     (2, 16, 16, 128, 128, 9, 2),    # stride 2 (output 16x16 from 32x32)
     (1, 28, 28, 64, 64, 9, 1),      # non power-of-two width (224/8)
-    (1, 4, 256, 64, 128, 9, 1),     # W > 128: row segments
+    (1, 4, 256, 64, 128, 9, 1),     # W > 128: row segments (halo-reuse kernel)
+    (2, 3, 128, 128, 256, 9, 1),    # W = 128, BN = 256 halo kernel, odd number of pixel tiles per image
+    (1, 5, 128, 64, 64, 1, 1),      # 1x1 at W = 128 (no halo), odd tile count -> out-of-range peer tile
 ]
 
 
@@ -84,12 +86,13 @@ def test_conv_plain(ops, impl, dtype, tol, case):
     assert rel_err(nchw(y), ref) < tol
 
 
+@pytest.mark.parametrize("H,W", [(16, 16), (3, 128)])
 @pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 2e-5), ("sm100", torch.bfloat16, 1e-2)])
-def test_conv_fused_resblock_tail(ops, impl, dtype, tol):
+def test_conv_fused_resblock_tail(ops, impl, dtype, tol, H, W):
     """conv2 of a ResidualBlock whose input is a virtual concat: 3x3 conv + two 1x1 shortcut
     K-segments + bias, and conv1 with the per-image time-embedding bias (dm1:94-103)."""
     torch.manual_seed(2)
-    B, H, W, c0, c1, cout = 2, 16, 16, 128, 64, 128
+    B, c0, c1, cout = 2, 128, 64, 128
     h = torch.randn(B, H, W, cout, device="cuda").to(dtype)
     xa = torch.randn(B, H, W, c0, device="cuda").to(dtype)
     xb = torch.randn(B, H, W, c1, device="cuda").to(dtype)
