@@ -5,7 +5,7 @@
 // One CTA per (image*head, 128-query tile); keys/values stream through in blocks of 128:
 //   warp 0   : TMA producer (Q once; K_j, V^T_j per block)
 //   warp 1   : tcgen05.mma issuer   S_j = Q K_j^T  (TMEM, double buffered),  O += P_j V_j  (TMEM)
-//   warps 2-5: online softmax, one query row per thread: S row TMEM -> registers, running max /
+//   warps 2-9: online softmax, one query row per thread PAIR (two warps split each block's keys): S row TMEM -> registers, running max /
 //              sum in fp32 (base-2 domain), P -> bf16 -> swizzled smem for the PV MMA; the O
 //              accumulator is rescaled in TMEM only when the running max grew by more than 2^8
 //              (lazy rescale); final O / l -> bf16 NHWC.
@@ -36,7 +36,7 @@ struct AttnPlan {
 };
 static_assert(sizeof(AttnPlan) <= ADVS_ATTN_PLAN_BYTES, "AttnPlan does not fit ADVS_ATTN_PLAN_BYTES");
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 8 softmax warps
 constexpr int kBQ = 128;   // queries per CTA
 constexpr int kBK = 128;   // keys per block
 constexpr float kLog2e = 1.4426950408889634f;
@@ -61,7 +61,7 @@ struct AttnCfg {
   static constexpr uint32_t off_v = off_k + kv_stages * k_bytes;
   static constexpr uint32_t off_p = off_v + kv_stages * v_bytes;
   static constexpr uint32_t off_bar = off_p + p_bytes;
-  static constexpr uint32_t smem_bytes = off_bar + 256 + 1024;
+  static constexpr uint32_t smem_bytes = off_bar + 128 + 2048 + 896;   // barriers + max/sum exchange + alignment slack (base is 128-B aligned)
   static constexpr uint32_t tmem_cols = 512;
   static constexpr uint32_t o_col = 256;
 };
@@ -102,7 +102,7 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     }
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
@@ -193,25 +193,36 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       }
     }
   } else {
-    // ================= softmax / correction / output (warps 2..5) =================
+    // ================= softmax / correction / output (warps 2..9) =================
+    // Two warps per TMEM lane quarter: warps 2-5 own keys [0,64) of each block, warps 6-9 keys [64,128).
+    // The softmax is MUFU-bound (one ex2 per score); two warps per scheduler let one warp's TMEM loads,
+    // smem stores and barrier waits hide behind the other's exponentials.  The row maximum is exchanged
+    // through shared memory once per block; the row sums are combined once at the end.
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     uint8_t* p_smem = smem + Cfg::off_p;
-    float m_used = -INFINITY;  // base-2 running max actually subtracted
-    float l = 0.f;
+    float* xch = reinterpret_cast<float*>(smem + Cfg::off_bar + 128);   // [2 parities][2 halves][128 rows]
+    constexpr int HB = kBK / 2;   // keys per warp
+    constexpr int HD = DH / 2;    // O columns per warp (rescale / output)
+    float m_used = -INFINITY;     // base-2 running max actually subtracted (identical in both partners)
+    float l = 0.f;                // this half's share of the row sum
     for (int j = 0; j < nblk; ++j) {
       mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      float s[kBK];
+      float s[HB];
 #pragma unroll
-      for (int c = 0; c < kBK / 32; ++c)
-        tmem_ld_32x32b_x32(lane_addr + (uint32_t)((j & 1) * kBK + c * 32), reinterpret_cast<uint32_t*>(s) + c * 32);
+      for (int c = 0; c < HB / 32; ++c)
+        tmem_ld_32x32b_x32(lane_addr + (uint32_t)((j & 1) * kBK + half * HB + c * 32), reinterpret_cast<uint32_t*>(s) + c * 32);
       tmem_wait_ld();
       float mx = s[0];
 #pragma unroll
-      for (int i = 1; i < kBK; ++i) mx = fmaxf(mx, s[i]);
-      mx *= kLog2e;
+      for (int i = 1; i < HB; ++i) mx = fmaxf(mx, s[i]);
+      // exchange the half-row maxima with the partner warp (same rows, other 64 keys)
+      xch[((j & 1) * 2 + half) * 128 + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
+      mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + row]) * kLog2e;
       float alpha = 1.f;
       bool grow = mx > m_used + kLazyThreshold;
       if (grow) {
@@ -220,7 +231,7 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       }
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < kBK; ++i) {
+      for (int i = 0; i < HB; ++i) {
         s[i] = fast_exp2(fmaf(s[i], kLog2e, -m_used));
         sum += s[i];
       }
@@ -229,49 +240,52 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       if (j > 0) {
         mbar_wait(o_done, (uint32_t)((j - 1) & 1));
         tc_fence_after();
-        if (__any_sync(0xffffffffu, grow)) {
+        if (__any_sync(0xffffffffu, grow)) {   // both partners take the same decision (same max); each rescales half of O
 #pragma unroll 1
-          for (int c = 0; c < DH / 32; ++c) {
+          for (int c = 0; c < HD / 32; ++c) {
             uint32_t r[32];
-            tmem_ld_32x32b_x32(lane_addr + Cfg::o_col + c * 32, r);
+            tmem_ld_32x32b_x32(lane_addr + Cfg::o_col + half * HD + c * 32, r);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x32(lane_addr + Cfg::o_col + c * 32, r);
+            tmem_st_32x32b_x32(lane_addr + Cfg::o_col + half * HD + c * 32, r);
           }
           tmem_wait_st();
         }
       }
-      // P -> bf16 -> smem, K-major SWIZZLE_128B: two slabs of [128 rows][64 keys]
+      // P -> bf16 -> smem, K-major SWIZZLE_128B: slab `half` of [128 rows][64 keys]
 #pragma unroll
-      for (int ch = 0; ch < kBK / 8; ++ch) {
+      for (int c8 = 0; c8 < HB / 8; ++c8) {
         uint4 v;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(s[ch * 8 + 0], s[ch * 8 + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(s[ch * 8 + 2], s[ch * 8 + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(s[ch * 8 + 4], s[ch * 8 + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(s[ch * 8 + 6], s[ch * 8 + 7]);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(s[c8 * 8 + 0], s[c8 * 8 + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(s[c8 * 8 + 2], s[c8 * 8 + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(s[c8 * 8 + 4], s[c8 * 8 + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(s[c8 * 8 + 6], s[c8 * 8 + 7]);
         v.x = *reinterpret_cast<uint32_t*>(&h0);
         v.y = *reinterpret_cast<uint32_t*>(&h1);
         v.z = *reinterpret_cast<uint32_t*>(&h2);
         v.w = *reinterpret_cast<uint32_t*>(&h3);
-        const int slab = ch >> 3, c8 = ch & 7;
-        *reinterpret_cast<uint4*>(p_smem + slab * (kBQ * 128) + row * 128 + ((c8 ^ (row & 7)) << 4)) = v;
+        *reinterpret_cast<uint4*>(p_smem + half * (kBQ * 128) + row * 128 + ((c8 ^ (row & 7)) << 4)) = v;
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // ---- output: O / l ----
+    // ---- output: O / l (row sum = both halves) ----
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");   // partner has finished reading the last max
+    xch[half * 128 + row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
+    l += xch[(half ^ 1) * 128 + row];
     mbar_wait(o_done, (uint32_t)((nblk - 1) & 1));
     tc_fence_after();
     const float inv = 1.f / l;
     const int b = bh / a.heads, head = bh - b * a.heads;
-    __nv_bfloat16* orow = a.o + ((size_t)b * a.T + q_tile * kBQ + row) * ((size_t)a.heads * DH) + (size_t)head * DH;
+    __nv_bfloat16* orow = a.o + ((size_t)b * a.T + q_tile * kBQ + row) * ((size_t)a.heads * DH) + (size_t)head * DH + half * HD;
 #pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
+    for (int c = 0; c < HD / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32b_x32(lane_addr + Cfg::o_col + c * 32, r);
+      tmem_ld_32x32b_x32(lane_addr + Cfg::o_col + half * HD + c * 32, r);
       tmem_wait_ld();
       uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
