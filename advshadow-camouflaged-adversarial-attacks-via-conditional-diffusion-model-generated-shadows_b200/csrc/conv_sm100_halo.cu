@@ -19,7 +19,7 @@ template <int BN>
 struct ConvCfgH {
   static constexpr uint32_t b_bytes = (BN / 2) * 128;          // this CTA's half of one tap's weight tile
   static constexpr uint32_t a_buf_bytes = 49 * 1024;           // >= 3 rows x 130 pixels x 128 B, 1 KB aligned
-  static constexpr int a_bufs = 2;
+  static constexpr int a_bufs = 2;                             // (3 buffers + a 5-deep weight ring measured slower)
   static constexpr int stages = (BN == 256) ? 6 : 10;          // weight-tile ring
   static constexpr uint32_t off_b = a_bufs * a_buf_bytes;
   static constexpr uint32_t off_bar = off_b + stages * b_bytes;

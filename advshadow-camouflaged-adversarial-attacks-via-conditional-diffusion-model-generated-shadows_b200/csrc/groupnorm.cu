@@ -102,26 +102,31 @@ __global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot
   }
 }
 
-// one warp per (image, group); the group's channels may straddle the two concatenated sources.
-// part_s layout: [B][parts_s][C_s][2]
-__global__ void k_gn_finalize(const float* __restrict__ part0, int c0, int parts0, const float* __restrict__ part1,
-                              int c1, int parts1, int groups, int HW, float eps, const float* __restrict__ gamma,
-                              const float* __restrict__ beta, float* __restrict__ scale_shift, int B) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (warp >= B * groups) return;
+// one 128-thread CTA per (image, group); the group's channels may straddle the two concatenated sources.
+// part_s layout: [B][parts_s][C_s][2].  Threads sweep (part, channel-in-group) pairs with the channel
+// fastest, so each warp reads contiguous float2 runs; fp64 accumulation, fixed reduction order.
+__global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ part0, int c0, int parts0,
+                                                     const float* __restrict__ part1, int c1, int parts1, int groups,
+                                                     int HW, float eps, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ scale_shift) {
+  __shared__ double red[2][4];
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
   const int Ctot = c0 + c1;
-  int b = warp / groups, g = warp % groups;
-  int cpg = Ctot / groups;
+  const int cpg = Ctot / groups;
+  const int glo = g * cpg, ghi = glo + cpg;
   double S = 0.0, SS = 0.0;
-  for (int cc = 0; cc < cpg; ++cc) {
-    const int c = g * cpg + cc;
-    const float* base;
-    int parts, C, cl;
-    if (c < c0) { base = part0; parts = parts0; C = c0; cl = c; }
-    else { base = part1; parts = parts1; C = c1; cl = c - c0; }
-    for (int p = lane; p < parts; p += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(base + (((size_t)b * parts + p) * C + cl) * 2);
+#pragma unroll
+  for (int src = 0; src < 2; ++src) {
+    const float* base = src == 0 ? part0 : part1;
+    const int C = src == 0 ? c0 : c1, parts = src == 0 ? parts0 : parts1, off = src == 0 ? 0 : c0;
+    int lo = glo > off ? glo : off;
+    int hi = ghi < off + C ? ghi : off + C;
+    const int n = hi - lo;
+    if (n <= 0 || parts <= 0) continue;
+    const float* p = base + ((size_t)b * parts * C + (lo - off)) * 2;
+    for (int it = threadIdx.x; it < parts * n; it += 128) {
+      const int pi = it / n, cc = it - pi * n;
+      const float2 v = *reinterpret_cast<const float2*>(p + ((size_t)pi * C + cc) * 2);
       S += (double)v.x;
       SS += (double)v.y;
     }
@@ -131,17 +136,23 @@ __global__ void k_gn_finalize(const float* __restrict__ part0, int c0, int parts
     S += __shfl_xor_sync(0xffffffffu, S, o);
     SS += __shfl_xor_sync(0xffffffffu, SS, o);
   }
-  double n = (double)HW * cpg;
-  double mean = S / n;
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = S;
+    red[1][threadIdx.x >> 5] = SS;
+  }
+  __syncthreads();
+  S = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+  SS = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+  const double n = (double)HW * cpg;
+  const double mean = S / n;
   double var = SS / n - mean * mean;
   if (var < 0.0) var = 0.0;
-  float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  float meanf = (float)mean;
-  for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
-    float sc = rstd * gamma[c];
-    float sh = beta[c] - meanf * sc;
-    scale_shift[((size_t)b * Ctot + c) * 2] = sc;
-    scale_shift[((size_t)b * Ctot + c) * 2 + 1] = sh;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  for (int c = glo + threadIdx.x; c < ghi; c += 128) {
+    const float sc = rstd * gamma[c];
+    const float sh = beta[c] - meanf * sc;
+    *reinterpret_cast<float2*>(scale_shift + ((size_t)b * Ctot + c) * 2) = make_float2(sc, sh);
   }
 }
 
@@ -221,9 +232,8 @@ static int gn_partial_impl(const void* x, int C, int B, int HW, float* part, cud
 static int gn_finalize_impl(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1, int B,
                             int HW, int groups, float eps, const float* gamma, const float* beta, float* scale_shift,
                             cudaStream_t st) {
-  int warps = B * groups;
-  k_gn_finalize<<<(warps * 32 + 127) / 128, 128, 0, st>>>(part0, c0, parts0, part1, c1, parts1, groups, HW, eps, gamma,
-                                                         beta, scale_shift, B);
+  k_gn_finalize<<<B * groups, 128, 0, st>>>(part0, c0, parts0, part1, c1, parts1, groups, HW, eps, gamma, beta,
+                                            scale_shift);
   ADVS_CHECK_LAUNCH("groupnorm_finalize");
   return ADVS_OK;
 }
