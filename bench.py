@@ -19,7 +19,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH = 2.04e9   # profiles/r01_summary.md (6 launches of k_conv_sm100<256>, batch 64)
+NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH = 0.595e9  # profiles/r01b_summary.md: mean over the 20 captured k_conv_sm100_2cta<256> launches
 METRIC = "shadowed images/sec (DDIM-50, 256x256)"
 UNIT = "images/s"
 
@@ -249,9 +249,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": sampler.launches_per_trajectory * args.steps + args.steps,
-            "roofline": {"kernel": "k_conv_sm100 (tcgen05 implicit-GEMM conv, all launches of one UNet forward)",
+            "roofline": {"kernel": "k_conv_sm100_2cta[_halo] (tcgen05 cta_group::2 implicit-GEMM conv, all launches of one UNet forward)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         # mean dram__bytes_read+write per captured conv launch, profiles/prof_r01_key_metrics.csv
+                         # mean dram__bytes_read+write per captured conv launch, profiles/prof_r01b_key_metrics.csv
+                         # (the capture covers 20 deep-level launches; "algorithmic_bytes_per_launch" averages all 105)
                          "traffic": NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH,
                          "algorithmic_bytes_per_launch": conv["bytes"] / max(conv["launches"], 1),
                          "peak_source": peak_src},

@@ -281,3 +281,45 @@ def test_attack_loop_single_rank(pkg):
     outside = ((xx - S / 2) ** 2 + (yy - S / 2) ** 2).sqrt() > 12.0
     assert torch.equal(res["shadowed"].cpu()[:, :, outside], clean[:, :, outside])
     model.release_engines()
+
+
+def test_attack_decisions_agree_with_reference_sampler(pkg):
+    """North-star end-to-end criterion for the bf16 path: attack-success decisions of a victim on images
+    sampled by the bf16 CUDA path vs by the reference algorithm (oracle port, fp32, CPU) from the same
+    noise must agree on >= 99 % of images.  128 images, dm1 UNet, 32x32, DDIM-10, composite included."""
+    from oracle import torch_port as P
+    model, _ = get_model(pkg, "dm1")
+    model.set_precision("bf16")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    B, S, n = 128, 32, 10
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(B, 3, S, S, generator=g)
+    clean = torch.rand(B, 3, S, S, generator=g)
+    fmask = (torch.rand(B, 1, S, S, generator=g) > 0.3).float()
+    centers = torch.rand(B, 2, generator=g) * S
+    radii = torch.rand(B, generator=g) * 8 + 6
+    labels = torch.randint(0, 37, (B,), generator=g)
+    torch.manual_seed(3)
+    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(4),
+                                 torch.nn.Flatten(), torch.nn.Linear(256, 37)).eval()
+    # CUDA path
+    from advshadow_b200.sampler import ShadowSampler
+    from advshadow_b200 import ops
+    sampler = ShadowSampler(model, gd, B, S, ddim_timesteps=n)
+    out = sampler(x_T, clean, fmask, centers, radii)
+    with torch.no_grad():
+        logits_gpu = victim.cuda()(out.cuda()).float()
+    flags_gpu, counts = ops.success_flags(logits_gpu, labels.cuda())
+    # reference algorithm on the CPU
+    params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        x0 = P.ddim_sample(params, P.DM1_CFG, P.cosine_alphas_cumprod(), x_T, n)
+        ref_imgs = torch.stack([P.apply_shadow(clean[i], centers[i], radii[i], fmask[i], 0.33,
+                                               perturb=lambda s, i=i: x0[i].clamp(0, 1)[None])[0][0] for i in range(B)])
+        flags_ref = victim.cpu()(ref_imgs).argmax(1) != labels
+    img_err = (out - ref_imgs).abs().max().item()
+    agree = (flags_gpu.cpu().bool() == flags_ref).float().mean().item()
+    print(f"bf16 DDIM-{n} + composite vs reference: max|image err| = {img_err:.3e}, decision agreement = {agree:.4f}, "
+          f"successes {int(counts[0])}/{int(counts[1])}")
+    assert agree >= 0.99
+    model.release_engines()
