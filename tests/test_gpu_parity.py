@@ -298,10 +298,11 @@ def test_attack_decisions_agree_with_reference_sampler(pkg):
     fmask = (torch.rand(B, 1, S, S, generator=g) > 0.3).float()
     centers = torch.rand(B, 2, generator=g) * S
     radii = torch.rand(B, generator=g) * 8 + 6
-    labels = torch.randint(0, 37, (B,), generator=g)
     torch.manual_seed(3)
-    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(4),
-                                 torch.nn.Flatten(), torch.nn.Linear(256, 37)).eval()
+    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, stride=2, padding=1), torch.nn.ReLU(), torch.nn.AvgPool2d(2),
+                                 torch.nn.Flatten(), torch.nn.Linear(16 * 8 * 8, 37)).eval()
+    with torch.no_grad():   # "true" label = the victim's decision on the clean image: success = the shadow flips it
+        labels = victim(clean).argmax(1)
     # CUDA path
     from advshadow_b200.sampler import ShadowSampler
     from advshadow_b200 import ops
@@ -316,10 +317,14 @@ def test_attack_decisions_agree_with_reference_sampler(pkg):
         x0 = P.ddim_sample(params, P.DM1_CFG, P.cosine_alphas_cumprod(), x_T, n)
         ref_imgs = torch.stack([P.apply_shadow(clean[i], centers[i], radii[i], fmask[i], 0.33,
                                                perturb=lambda s, i=i: x0[i].clamp(0, 1)[None])[0][0] for i in range(B)])
-        flags_ref = victim.cpu()(ref_imgs).argmax(1) != labels
+        pred_ref = victim.cpu()(ref_imgs).argmax(1)
+        flags_ref = pred_ref != labels
     img_err = (out - ref_imgs).abs().max().item()
     agree = (flags_gpu.cpu().bool() == flags_ref).float().mean().item()
+    same_class = (logits_gpu.argmax(1).cpu() == pred_ref).float().mean().item()
     print(f"bf16 DDIM-{n} + composite vs reference: max|image err| = {img_err:.3e}, decision agreement = {agree:.4f}, "
-          f"successes {int(counts[0])}/{int(counts[1])}")
-    assert agree >= 0.99
+          f"same predicted class = {same_class:.4f}, successes {int(counts[0])}/{int(counts[1])} (reference {int(flags_ref.sum())}), "
+          f"{pred_ref.unique().numel()} distinct predicted classes")
+    assert pred_ref.unique().numel() >= 4 and 0 < int(flags_ref.sum()) < B, "degenerate victim: the check would be vacuous"
+    assert agree >= 0.99 and same_class >= 0.99
     model.release_engines()
