@@ -75,6 +75,15 @@ SIGNATURES = {
     "advs_gaussian_blur5": (C.c_int, [_vp, _vp, _i, _i, _i, _vp]),
     "advs_shadow_composite": (C.c_int, [_vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "advs_shadow_composite_generated": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "advs_maxpool2x2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "advs_upsample_bilinear2x": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "advs_copy_channels": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, _vp]),
+    "advs_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
+    "advs_groupnorm_apply_ex": (C.c_int, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp]),
+    "advs_activation": (C.c_int, [_vp, _vp, _sz, _i, _i, _vp]),
+    "advs_pos_encoding": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "advs_cfg_lerp": (C.c_int, [_vp, _vp, _f, _vp, _sz, _vp]),
+    "advs_to_uint8": (C.c_int, [_vp, _vp, _sz, _vp]),
     "advs_success_flags": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 

@@ -1,0 +1,433 @@
+"""IDDM class-conditional UNet + classifier-free-guidance DDIM sampler on the B200 kernels.
+
+Reference: model/networks/unet.py:17-128 (`UNet`), model/networks/base.py:12-68 (`BaseNet`: label embedding, sin|cos
+position encoding), model/modules/{conv,block,attention}.py, model/samples/{base,ddim}.py (`DDIMDiffusion.sample`).
+Same constructor arguments, attributes and state_dict keys as the reference classes; forward / sample run on the C-ABI
+kernels (implicit-GEMM convs and token linears, attention, GroupNorm(1,C), LayerNorm, MaxPool, bilinear upsample, CFG lerp).
+This path is the "secondary" one of the survey: it is built for parity first; its attention at head dims 16/32 uses the
+SIMT kernel (the tcgen05 flash kernel covers head dims 64/128/256).  CUDA only, inference only -- no fallback.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+from tqdm import tqdm
+
+from . import _capi as capi
+
+_ACT = {"silu": 1, "gelu": 2}
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter holders with the reference's module tree (=> identical state_dict keys and seeded initialisation)
+# ---------------------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError("advshadow_b200.iddm sub-modules are parameter holders; call UNet.forward")
+
+
+def _act_module(name):
+    return {"relu": nn.ReLU(), "relu6": nn.ReLU6(), "silu": nn.SiLU(), "lrelu": nn.LeakyReLU(0.1), "gelu": nn.GELU()}.get(
+        name, nn.SiLU())
+
+
+class DoubleConv(_Holder):                      # conv.py:20-66
+    def __init__(self, in_channels, out_channels, mid_channels=None, residual=False, act="silu"):
+        super().__init__()
+        self.residual = residual
+        mid_channels = mid_channels or out_channels
+        self.act = act
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=3, padding=1, bias=False), nn.GroupNorm(1, mid_channels),
+            _act_module(act),
+            nn.Conv2d(mid_channels, out_channels, kernel_size=3, padding=1, bias=False), nn.GroupNorm(1, out_channels))
+
+
+class DownBlock(_Holder):                       # block.py:15-46
+    def __init__(self, in_channels, out_channels, emb_channels=256, act="silu"):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, in_channels, residual=True, act=act),
+                                          DoubleConv(in_channels, out_channels, act=act))
+        self.emb_layer = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, out_channels))
+
+
+class UpBlock(_Holder):                         # block.py:49-78
+    def __init__(self, in_channels, out_channels, emb_channels=256, act="silu"):
+        super().__init__()
+        self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+        self.conv = nn.Sequential(DoubleConv(in_channels, in_channels, residual=True, act=act),
+                                  DoubleConv(in_channels, out_channels, mid_channels=in_channels // 2, act=act))
+        self.emb_layer = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, out_channels))
+
+
+class SelfAttention(_Holder):                   # attention.py:12-53
+    def __init__(self, channels, size, act="silu"):
+        super().__init__()
+        self.channels, self.size = channels, size
+        self.mha = nn.MultiheadAttention(embed_dim=channels, num_heads=4, batch_first=True)
+        self.ln = nn.LayerNorm([channels])
+        self.ff_self = nn.Sequential(nn.LayerNorm([channels]), nn.Linear(channels, channels), _act_module(act),
+                                     nn.Linear(channels, channels))
+
+
+class UNet(nn.Module):
+    """Drop-in for model/networks/unet.py `UNet` (label-conditional when num_classes is given)."""
+
+    def __init__(self, in_channel=3, out_channel=3, channel=None, time_channel=256, num_classes=None, image_size=64,
+                 device="cpu", act="silu"):
+        super().__init__()
+        self.in_channel, self.out_channel = in_channel, out_channel
+        self.channel = channel if channel is not None else [32, 64, 128, 256, 512, 1024]   # base.py:44-53
+        self.time_channel, self.num_classes, self.image_size, self.device, self.act = (time_channel, num_classes,
+                                                                                       image_size, device, act)
+        if num_classes is not None:
+            self.label_emb = nn.Embedding(num_embeddings=num_classes, embedding_dim=time_channel)
+        ch = self.channel
+        self.inc = DoubleConv(in_channel, ch[1], act=act)
+        self.down1 = DownBlock(ch[1], ch[2], act=act)
+        self.sa1 = SelfAttention(ch[2], int(image_size / 2), act=act)
+        self.down2 = DownBlock(ch[2], ch[3], act=act)
+        self.sa2 = SelfAttention(ch[3], int(image_size / 4), act=act)
+        self.down3 = DownBlock(ch[3], ch[3], act=act)
+        self.sa3 = SelfAttention(ch[3], int(image_size / 8), act=act)
+        self.bot1 = DoubleConv(ch[3], ch[4], act=act)
+        self.bot2 = DoubleConv(ch[4], ch[4], act=act)
+        self.bot3 = DoubleConv(ch[4], ch[3], act=act)
+        self.up1 = UpBlock(ch[4], ch[2], act=act)
+        self.sa4 = SelfAttention(ch[2], int(image_size / 4), act=act)
+        self.up2 = UpBlock(ch[3], ch[1], act=act)
+        self.sa5 = SelfAttention(ch[1], int(image_size / 2), act=act)
+        self.up3 = UpBlock(ch[2], ch[1], act=act)
+        self.sa6 = SelfAttention(ch[1], int(image_size), act=act)
+        self.outc = nn.Conv2d(ch[1], out_channel, kernel_size=1)
+        self.precision = "fp32"     # parity-first default on this path; "bf16" is opt-in
+        self._engines = {}
+
+    def set_precision(self, precision):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        return self
+
+    def _apply(self, fn, *a, **k):
+        self._engines = {}
+        return super()._apply(fn, *a, **k)
+
+    def release_engines(self):
+        self._engines.clear()
+
+    def engine(self, B, precision=None):
+        precision = precision or self.precision
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("advshadow_b200.iddm.UNet runs on CUDA only (there is no CPU path)")
+        if self.act not in _ACT:
+            raise NotImplementedError(f"activation {self.act!r}: the B200 path implements 'silu' and 'gelu'")
+        tok = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (B, precision, dev.index)
+        hit = self._engines.get(key)
+        if hit is None or hit[1] != tok:
+            self._engines[key] = (_IddmEngine(self, B, precision), tok)
+        return self._engines[key][0]
+
+    def forward(self, x, time, y=None):
+        """eps = UNet(x[N,3,S,S], time[N], y[N] | None)  (unet.py:95-128).  CUDA, inference only."""
+        if not x.is_cuda:
+            raise RuntimeError("advshadow_b200.iddm.UNet.forward needs CUDA tensors (no CPU path)")
+        if x.shape[-1] != self.image_size or x.shape[-2] != self.image_size:
+            raise ValueError(f"SelfAttention hard-codes image_size={self.image_size} (attention.py:46); got {tuple(x.shape)}")
+        return self.engine(x.shape[0]).forward(x.float(), time, y)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class _IddmEngine:
+    """Static buffers + launch list for one (batch, precision); built by walking the reference's forward."""
+
+    def __init__(self, net: UNet, B, precision):
+        self.lib = capi.lib()
+        self.net, self.B, self.precision = net, B, precision
+        self.dev = next(net.parameters()).device
+        self.dt = capi.BF16 if precision == "bf16" else capi.F32
+        self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        with torch.cuda.device(self.dev):
+            self.sm100 = precision == "bf16" and bool(self.lib.advs_device_is_sm100())
+        self.act = _ACT[net.act]
+        self.keep, self.L = [], []
+        S, tc = net.image_size, net.time_channel
+        dev = self.dev
+        self.x = torch.zeros(B, net.in_channel, S, S, dtype=torch.float32, device=dev)
+        self.eps = torch.zeros(B, net.out_channel, S, S, dtype=torch.float32, device=dev)
+        self.t = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.y = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.time = torch.zeros(B, tc, dtype=torch.float32, device=dev)
+        # base.py:63: 1 / 10000^(arange(0, C, 2) / C), evaluated like the reference and uploaded
+        self.inv_freq = (1.0 / (10000 ** (torch.arange(start=0, end=tc, step=2).float() / tc))).to(dev)
+        self.label_w = net.label_emb.weight.detach().float().contiguous() if net.num_classes is not None else None
+        with torch.cuda.device(dev):
+            self._build()
+
+    # ---- helpers -------------------------------------------------------------------------------------------
+    def buf(self, *shape, dtype=None):
+        t = torch.empty(*shape, dtype=dtype or self.tdt, device=self.dev)
+        self.keep.append(t)
+        return t
+
+    def add(self, fn_name, *args):
+        self.L.append((getattr(self.lib, fn_name), args, fn_name))
+
+    def pack(self, w4d):
+        """OIHW fp32 parameter -> [O][taps][I] in the engine dtype."""
+        w = w4d.detach().float().contiguous()
+        O, I, kh, kw = w.shape
+        dst = self.buf(O, kh * kw, I)
+        capi.call("advs_pack_conv_weight", w.data_ptr(), dst.data_ptr(), O, I, kh, kw, self.dt, _st())
+        self.keep.append(w)
+        return dst
+
+    def f32(self, p):
+        t = p.detach().float().contiguous()
+        self.keep.append(t)
+        return t
+
+    def conv(self, x, B, H, W, cin, w_packed, cout, bias=None, residual=None, qkv_heads=None, nchw_out=None, cout_valid=None):
+        cp = capi.ConvParams()
+        taps = w_packed.shape[1]
+        cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, w_packed.shape[0], 1, 1
+        cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), w_packed.data_ptr(), cin, taps
+        cp.bias = bias.data_ptr() if bias is not None else None
+        cp.residual = residual.data_ptr() if residual is not None else None
+        cp.dtype = self.dt
+        out = None
+        if qkv_heads:
+            dh = cout // (3 * qkv_heads)
+            T = H * W
+            q, k, vt = self.buf(B, qkv_heads, T, dh), self.buf(B, qkv_heads, T, dh), self.buf(B, qkv_heads, dh, T)
+            cp.out_mode, cp.q, cp.k, cp.vt, cp.heads = 1, q.data_ptr(), k.data_ptr(), vt.data_ptr(), qkv_heads
+            cp.qk_scale = 1.0 / math.sqrt(math.sqrt(dh))     # MHA scales q by dh^-1/2; split evenly over q and k
+            out = (q, k, vt)
+            dh_ok = dh % 32 == 0
+        elif nchw_out is not None:
+            cp.out_mode, cp.y, cp.cout_valid = 2, nchw_out.data_ptr(), cout_valid
+            out = nchw_out
+            dh_ok = True
+        else:
+            out = self.buf(B, H, W, cout)
+            cp.out_mode, cp.y = 0, out.data_ptr()
+            dh_ok = True
+        self.keep.append(cp)
+        if self.sm100 and cin % 64 == 0 and w_packed.shape[0] % 64 == 0 and dh_ok:
+            pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+            capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+            self.keep.append(pb)
+            self.add("advs_conv_sm100_launch", pb.ptr)
+        else:
+            self.add("advs_conv_simt", C.byref(cp))
+        return out
+
+    def gn(self, x, B, HW, Cc, gnmod, act=0, residual=None, emb=None):
+        ss = self.buf(B, Cc, 2, dtype=torch.float32)
+        wsb = int(self.lib.advs_groupnorm_workspace_bytes(B, HW, Cc))
+        ws = self.buf(max(wsb, 4), dtype=torch.uint8)
+        g, b = self.f32(gnmod.weight), self.f32(gnmod.bias)
+        self.add("advs_groupnorm_stats", x.data_ptr(), Cc, None, 0, B, HW, 1, float(gnmod.eps), g.data_ptr(), b.data_ptr(),
+                 ss.data_ptr(), ws.data_ptr(), wsb, self.dt)
+        y = self.buf(*x.shape)
+        self.add("advs_groupnorm_apply_ex", x.data_ptr(), B, HW, Cc, ss.data_ptr(),
+                 residual.data_ptr() if residual is not None else None,
+                 emb.data_ptr() if emb is not None else None, Cc if emb is not None else 0, act, y.data_ptr(), self.dt)
+        return y
+
+    def double_conv(self, x, B, H, W, cin, dc: DoubleConv, emb=None, first_is_stem=False):
+        c1, g1, _, c2, g2 = dc.double_conv
+        mid, cout = c1.out_channels, c2.out_channels
+        if first_is_stem:      # Cin = 3: fp32 NCHW input, direct kernel
+            w = self.f32(c1.weight)
+            wp = self.buf(mid, 9, cin, dtype=torch.float32)
+            capi.call("advs_pack_conv_weight", w.data_ptr(), wp.data_ptr(), mid, cin, 3, 3, capi.F32, _st())
+            h = self.buf(B, H, W, mid)
+            self.add("advs_conv3x3_stem", x.data_ptr(), wp.data_ptr(), None, h.data_ptr(), B, H, W, cin, mid, self.dt)
+        else:
+            h = self.conv(x, B, H, W, cin, self.pack(c1.weight), mid)
+        h = self.gn(h, B, H * W, mid, g1, act=self.act)
+        h = self.conv(h, B, H, W, mid, self.pack(c2.weight), cout)
+        if dc.residual:        # act(x + double_conv(x))  (conv.py:49-63)
+            return self.gn(h, B, H * W, cout, g2, act=self.act, residual=x)
+        return self.gn(h, B, H * W, cout, g2, act=0, emb=emb)
+
+    def emb_proj(self, block):
+        lin = block.emb_layer[1]
+        out = self.buf(self.B, lin.out_features, dtype=torch.float32)
+        w, b = self.f32(lin.weight), self.f32(lin.bias)
+        self.add("advs_linear_f32", self.time.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), self.B, lin.in_features,
+                 lin.out_features, 1, 0)
+        return out
+
+    def down(self, x, H, W, cin, blk: DownBlock):
+        B = self.B
+        p = self.buf(B, H // 2, W // 2, cin)
+        self.add("advs_maxpool2x2", x.data_ptr(), p.data_ptr(), B, H, W, cin, self.dt)
+        emb = self.emb_proj(blk)
+        h = self.double_conv(p, B, H // 2, W // 2, cin, blk.maxpool_conv[1])
+        return self.double_conv(h, B, H // 2, W // 2, cin, blk.maxpool_conv[2], emb=emb)
+
+    def up(self, x, skip, H, W, cx, cs, blk: UpBlock):
+        """x [B,H,W,cx] is upsampled to 2H x 2W and concatenated AFTER skip [B,2H,2W,cs] (block.py:72-73)."""
+        B = self.B
+        ct = cs + cx
+        cat = self.buf(B, 2 * H, 2 * W, ct)
+        self.add("advs_copy_channels", skip.data_ptr(), cat.data_ptr(), B * 4 * H * W, cs, ct, 0, self.dt)
+        self.add("advs_upsample_bilinear2x", x.data_ptr(), cat.data_ptr(), B, H, W, cx, ct, cs, self.dt)
+        emb = self.emb_proj(blk)
+        h = self.double_conv(cat, B, 2 * H, 2 * W, ct, blk.conv[0])
+        return self.double_conv(h, B, 2 * H, 2 * W, ct, blk.conv[1], emb=emb)
+
+    def sa(self, x, H, W, Cc, m: SelfAttention):
+        B, T, heads = self.B, H * W, 4
+        dh = Cc // heads
+        ln = self.buf(B, H, W, Cc)
+        self.add("advs_layernorm", x.data_ptr(), self.f32(m.ln.weight).data_ptr(), self.f32(m.ln.bias).data_ptr(),
+                 ln.data_ptr(), B * T, Cc, float(m.ln.eps), self.dt)
+        # in_proj rows are [q | k | v] blocks; the qkv epilogue wants per-head [q_h | k_h | v_h]
+        idx = torch.arange(3 * Cc, device=self.dev).view(3, heads, dh).permute(1, 0, 2).reshape(-1)
+        w_in = m.mha.in_proj_weight.detach().float()[idx].contiguous().view(3 * Cc, Cc, 1, 1)
+        b_in = m.mha.in_proj_bias.detach().float()[idx].contiguous()
+        self.keep.append(b_in)
+        q, k, vt = self.conv(ln, B, H, W, Cc, self.pack(w_in), 3 * Cc, bias=b_in, qkv_heads=heads)
+        o = self.buf(B, T, Cc)
+        if self.sm100 and dh in (64, 128, 256) and T % 128 == 0:
+            pb = capi.PlanBuffer(capi.ATTN_PLAN_BYTES)
+            capi.call("advs_attention_sm100_plan", q.data_ptr(), k.data_ptr(), vt.data_ptr(), o.data_ptr(), B, heads, T, dh, pb.ptr)
+            self.keep.append(pb)
+            self.add("advs_attention_sm100_launch", pb.ptr)
+        else:
+            wsb = int(self.lib.advs_attention_simt_workspace_bytes(B, heads, T))
+            ws = self.buf(wsb, dtype=torch.uint8)
+            self.add("advs_attention_simt", q.data_ptr(), k.data_ptr(), vt.data_ptr(), o.data_ptr(), B, heads, T, dh,
+                     ws.data_ptr(), wsb, self.dt)
+        wo = m.mha.out_proj.weight.detach().float().view(Cc, Cc, 1, 1)
+        av = self.conv(o, B, H, W, Cc, self.pack(wo), Cc, bias=self.f32(m.mha.out_proj.bias), residual=x)
+        f = self.buf(B, H, W, Cc)
+        ln2 = m.ff_self[0]
+        self.add("advs_layernorm", av.data_ptr(), self.f32(ln2.weight).data_ptr(), self.f32(ln2.bias).data_ptr(), f.data_ptr(),
+                 B * T, Cc, float(ln2.eps), self.dt)
+        h = self.conv(f, B, H, W, Cc, self.pack(m.ff_self[1].weight.detach().float().view(Cc, Cc, 1, 1)), Cc,
+                      bias=self.f32(m.ff_self[1].bias))
+        ha = self.buf(B, H, W, Cc)
+        self.add("advs_activation", h.data_ptr(), ha.data_ptr(), B * T * Cc, self.act, self.dt)
+        return self.conv(ha, B, H, W, Cc, self.pack(m.ff_self[3].weight.detach().float().view(Cc, Cc, 1, 1)), Cc,
+                         bias=self.f32(m.ff_self[3].bias), residual=av)
+
+    def _build(self):
+        n, B, S = self.net, self.B, self.net.image_size
+        ch = n.channel
+        x1 = self.double_conv(self.x, B, S, S, n.in_channel, n.inc, first_is_stem=True)
+        x2 = self.sa(self.down(x1, S, S, ch[1], n.down1), S // 2, S // 2, ch[2], n.sa1)
+        x3 = self.sa(self.down(x2, S // 2, S // 2, ch[2], n.down2), S // 4, S // 4, ch[3], n.sa2)
+        x4 = self.sa(self.down(x3, S // 4, S // 4, ch[3], n.down3), S // 8, S // 8, ch[3], n.sa3)
+        b = self.double_conv(x4, B, S // 8, S // 8, ch[3], n.bot1)
+        b = self.double_conv(b, B, S // 8, S // 8, ch[4], n.bot2)
+        b = self.double_conv(b, B, S // 8, S // 8, ch[4], n.bot3)
+        u = self.sa(self.up(b, x3, S // 8, S // 8, ch[3], ch[3], n.up1), S // 4, S // 4, ch[2], n.sa4)
+        u = self.sa(self.up(u, x2, S // 4, S // 4, ch[2], ch[2], n.up2), S // 2, S // 2, ch[1], n.sa5)
+        u = self.sa(self.up(u, x1, S // 2, S // 2, ch[1], ch[1], n.up3), S, S, ch[1], n.sa6)
+        # outc: 1x1 conv -> fp32 NCHW (zero-padded to a 64-row weight tile on the tcgen05 path)
+        w = n.outc.weight.detach().float().contiguous()
+        pad = 64 if (self.sm100 and ch[1] % 64 == 0) else n.out_channel
+        wp = torch.zeros(pad, 1, ch[1], dtype=self.tdt, device=self.dev)
+        wp[:n.out_channel] = self.pack(w)
+        bp = torch.zeros(pad, dtype=torch.float32, device=self.dev)
+        bp[:n.out_channel] = n.outc.bias.detach().float()
+        self.keep += [wp, bp]
+        self.conv(u, B, S, S, ch[1], wp, pad, bias=bp, nchw_out=self.eps, cout_valid=n.out_channel)
+
+    # ---- execution -----------------------------------------------------------------------------------------
+    def run(self, use_labels):
+        st = _st()
+        capi.call("advs_pos_encoding", self.t.data_ptr(), self.B, self.inv_freq.data_ptr(), self.net.time_channel // 2,
+                  self.y.data_ptr() if use_labels else None, self.label_w.data_ptr() if use_labels else None,
+                  self.time.data_ptr(), st)
+        err = self.lib.advs_last_error
+        for fn, args, name in self.L:
+            rc = fn(*args, st)
+            if rc:
+                raise capi.AdvsError(f"{name} failed (rc={rc}): {err().decode()}")
+
+    def forward(self, x, time, y=None):
+        with torch.cuda.device(self.dev):
+            self.x.copy_(x)
+            self.t.copy_(time.reshape(-1).to(torch.int64))
+            if y is not None:
+                if self.label_w is None:
+                    raise ValueError("labels given but the network was built without num_classes")
+                self.y.copy_(y.reshape(-1).to(torch.int64))
+            self.run(y is not None)
+            return self.eps.clone()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class DDIMDiffusion:
+    """model/samples/ddim.py `DDIMDiffusion` (+ BaseDiffusion's linear schedule, base.py:18-49)."""
+
+    def __init__(self, noise_steps=1000, sample_steps=500, beta_start=1e-4, beta_end=2e-2, img_size=64, device="cpu"):
+        self.noise_steps, self.beta_start, self.beta_end, self.img_size, self.device = (noise_steps, beta_start, beta_end,
+                                                                                        img_size, device)
+        self.beta = torch.linspace(start=beta_start, end=beta_end, steps=noise_steps).to(device)
+        self.alpha = 1. - self.beta
+        self.alpha_hat = torch.cumprod(input=self.alpha, dim=0)
+        self.sample_steps, self.eta = sample_steps, 0
+        ts = torch.arange(0, noise_steps, (noise_steps // sample_steps)).long() + 1
+        ts = reversed(torch.cat((torch.tensor([0], dtype=torch.long), ts)))
+        self.time_step = list(zip(ts[:-1], ts[1:]))
+
+    def _coefficients(self):
+        """Per step [sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt((1-a_prev) - c1^2), c1, 0,0,0] with the reference's fp32
+        op order (ddim.py:70-94); eta = 0 => c1 = 0."""
+        ah = self.alpha_hat.detach().float().cpu()
+        rows = []
+        for i, p_i in self.time_step:
+            a_t, a_p = ah[int(i)], ah[int(p_i)]
+            c1 = self.eta * torch.sqrt((1 - a_t / a_p) * (1 - a_p) / (1 - a_t))
+            c2 = torch.sqrt((1 - a_p) - c1 ** 2)
+            z = torch.zeros(())
+            rows.append(torch.stack([torch.sqrt(1 - a_t), torch.sqrt(a_t), torch.sqrt(a_p), c2, c1.float(), z, z, z]))
+        return torch.stack(rows).float().contiguous()
+
+    def sample(self, model, n, labels=None, cfg_scale=None, *, x_T=None, return_float=False):
+        """DDIM sampling with optional classifier-free guidance; returns uint8 [n,3,S,S] on the device like the
+        reference (ddim.py:48-100).  `x_T` / `return_float` are extension kwargs for parity tests."""
+        if not isinstance(model, UNet):
+            raise TypeError("advshadow_b200.iddm.DDIMDiffusion.sample needs an advshadow_b200.iddm.UNet")
+        model.eval()
+        dev = next(model.parameters()).device
+        eng = model.engine(n)
+        S = self.img_size
+        with torch.no_grad(), torch.cuda.device(dev):
+            x = (torch.randn((n, 3, S, S)) if x_T is None else x_T.float()).to(dev).contiguous()
+            coef = self._coefficients().to(dev)
+            step = torch.zeros(1, dtype=torch.int32, device=dev)
+            uncond = torch.empty_like(x)
+            guided = torch.empty_like(x)
+            for i, _ in tqdm(self.time_step, disable=None):
+                t = (torch.ones(n) * i).long().to(dev)
+                if labels is None and cfg_scale is None:
+                    eps = eng.forward(x, t)
+                else:
+                    eps = eng.forward(x, t, labels)
+                    if cfg_scale > 0:
+                        uncond.copy_(eng.forward(x, t, None))
+                        capi.call("advs_cfg_lerp", uncond.data_ptr(), eps.data_ptr(), C.c_float(float(cfg_scale)),
+                                  guided.data_ptr(), x.numel(), _st())
+                        eps = guided
+                capi.call("advs_ddim_step", x.data_ptr(), eps.data_ptr(), None, x.data_ptr(), x.numel(), coef.data_ptr(),
+                          step.data_ptr(), 1, 1, _st())
+            model.train()          # the reference leaves the model in train() mode (ddim.py:95)
+            if return_float:
+                return x
+            out = torch.empty(x.shape, dtype=torch.uint8, device=dev)
+            capi.call("advs_to_uint8", x.data_ptr(), out.data_ptr(), x.numel(), _st())
+            return out

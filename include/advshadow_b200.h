@@ -222,6 +222,32 @@ int advs_shadow_composite_generated(const float* img, const float* x_final, cons
                                     const float* radii, const float* feature_mask, int Cm,
                                     float* out, int B, int C, int H, int W, void* stream);
 
+/* ---- IDDM class-conditional UNet + CFG DDIM (model/networks/unet.py:17-128, model/modules/*.py,
+ *      model/samples/ddim.py:48-100): the bandwidth ops not shared with the diff_model path ------------------ */
+/* nn.MaxPool2d(2) over NHWC (block.py:25) */
+int advs_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (block.py:56) into channels [y_coff, y_coff+C) of
+ * y [B,2H,2W,y_cstride]; advs_copy_channels places the skip tensor in the same concat buffer (block.py:73) */
+int advs_upsample_bilinear2x(const void* x, void* y, int B, int H, int W, int C, int y_cstride, int y_coff, int dtype,
+                             void* stream);
+int advs_copy_channels(const void* x, void* y, size_t npix, int C, int y_cstride, int y_coff, int dtype, void* stream);
+/* nn.LayerNorm([C]) per token (attention.py:29,31) */
+int advs_layernorm(const void* x, const float* gamma, const float* beta, void* y, size_t rows, int C, float eps,
+                   int dtype, void* stream);
+/* y = act(x*scale + shift (+ residual)) (+ emb[b,c]); act: 0 none, 1 SiLU, 2 GELU(erf).  DoubleConv's GroupNorm(1,C)
+ * + activation + residual form (conv.py:40-66) and the "x + emb" of Down/UpBlock (block.py:44-46, 76-78) */
+int advs_groupnorm_apply_ex(const void* x, int B, int HW, int C, const float* scale_shift, const void* residual,
+                            const float* emb, int emb_stride, int act, void* y, int dtype, void* stream);
+int advs_activation(const void* x, void* y, size_t n, int act, int dtype, void* stream);
+/* BaseNet.pos_encoding: out[i] = [sin(t_i f_j) | cos(t_i f_j)] (+ label_emb[labels[i]] when labels != NULL);
+ * inv_freq[half] is the reference's 1/10000^(arange(0,C,2)/C) table (base.py:63), evaluated by the host */
+int advs_pos_encoding(const int64_t* t, int nt, const float* inv_freq, int half, const int64_t* labels,
+                      const float* label_emb, float* out, void* stream);
+/* torch.lerp(uncond, cond, w): classifier-free guidance (ddim.py:89) */
+int advs_cfg_lerp(const float* uncond, const float* cond, float w, float* out, size_t n, void* stream);
+/* ((x + 1) * 0.5 * 255).type(uint8) without clamp (ddim.py:97-99) */
+int advs_to_uint8(const float* x, uint8_t* out, size_t n, void* stream);
+
 /* ---- attack-success decision (ASR_fast.py:101-126) --------------------------------------- */
 /* flags[b] = argmax_c logits[b,c] != labels[b] (first max wins, like torch.max);
  * counts[0] += number of successes, counts[1] += B. */

@@ -190,6 +190,46 @@ def stochastic_cases():
     return out
 
 
+def iddm_cases():
+    """IDDM class-conditional UNet (unet.py:17-128) and DDIMDiffusion.sample with CFG (ddim.py:48-100)."""
+    UNet, DDIM = R.iddm()
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    for size, B in ((32, 2), (64, 1)):
+        torch.manual_seed(0)
+        net = UNet(num_classes=37, image_size=size, device="cpu").eval()
+        x = torch.randn(B, 3, size, size, generator=g)
+        t = torch.tensor([777, 12][:B])
+        y = torch.tensor([3, 36][:B])
+        with torch.no_grad():
+            out[f"fwd_{size}"] = dict(x=x, t=t, y=y, eps_cond=net(x, t, y), eps_uncond=net(x, t, None),
+                                      checksum=weight_checksum(net))
+    # CFG sampling, 5 steps of 1000, 32x32, with a per-call trace of the denoiser
+    torch.manual_seed(0)
+    net = UNet(num_classes=37, image_size=32, device="cpu").eval()
+    trace = []
+    real_forward = net.forward
+
+    def traced(x, time, y=None):
+        e = real_forward(x, time, y)
+        trace.append((x.clone(), time.clone(), None if y is None else y.clone(), e.clone()))
+        return e
+
+    net.forward = traced
+    ddim = DDIM(noise_steps=1000, sample_steps=5, img_size=32, device="cpu")
+    labels = torch.tensor([5, 20])
+    torch.manual_seed(5)
+    x_T = torch.randn((2, 3, 32, 32))
+    torch.manual_seed(5)                       # the reference draws x_T with the global CPU generator (ddim.py:61)
+    img = ddim.sample(net, 2, labels=labels, cfg_scale=3)
+    out["sample"] = dict(x_T=x_T, labels=labels, cfg_scale=3, sample_steps=5, image=img,
+                         trace_x=torch.stack([t[0] for t in trace]), trace_t=torch.stack([t[1] for t in trace]),
+                         trace_has_y=torch.tensor([t[2] is not None for t in trace]),
+                         trace_eps=torch.stack([t[3] for t in trace]))
+    assert torch.equal(trace[0][0], x_T)
+    return out
+
+
 def schedules():
     dm1, dm2 = R.dm1(), R.dm2()
     out = {}
@@ -206,5 +246,6 @@ if __name__ == "__main__":
     torch.save(shadow_cases(), os.path.join(OUT, "shadow.pt"))
     torch.save(schedules(), os.path.join(OUT, "schedules.pt"))
     torch.save(stochastic_cases(), os.path.join(OUT, "stochastic.pt"))
+    torch.save(iddm_cases(), os.path.join(OUT, "iddm.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

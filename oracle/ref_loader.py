@@ -64,3 +64,13 @@ def dm1():
 def dm2():
     """reference ddim2/diff_model2.py (bigger UNet defaults, apply_shadow dm2:615-654)."""
     return _load("dm2", "ddim2/diff_model2.py")
+
+
+def iddm():
+    """(UNet, DDIMDiffusion) of the vendored IDDM tree: model/networks/unet.py, model/samples/ddim.py."""
+    install_stubs()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    from model.networks.unet import UNet          # noqa: E402
+    from model.samples.ddim import DDIMDiffusion  # noqa: E402
+    return UNet, DDIMDiffusion
