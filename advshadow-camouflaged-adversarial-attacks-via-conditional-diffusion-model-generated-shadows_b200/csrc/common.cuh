@@ -40,6 +40,8 @@ template <> struct Vec8<float> {
     *reinterpret_cast<float4*>(p) = a;
     *reinterpret_cast<float4*>(p + 4) = b;
   }
+  __device__ __forceinline__ void load_stream(const float* p) { load(p); }
+  __device__ __forceinline__ void store_stream(float* p) const { store(p); }
   __device__ __forceinline__ void to_float(float* f) const {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   }
@@ -52,6 +54,14 @@ template <> struct Vec8<__nv_bfloat16> {
   uint4 v;
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  // streaming variants for read-once / write-once tensors (GroupNorm apply): bypass L1, evict-first in L2
+  __device__ __forceinline__ void load_stream(const __nv_bfloat16* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  }
+  __device__ __forceinline__ void store_stream(__nv_bfloat16* p) const {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
   __device__ __forceinline__ void to_float(float* f) const {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll

@@ -199,19 +199,19 @@ __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict
     }
     Vec8<T> vo;
     vo.from_float(f);
-    vo.store(dst + (size_t)p * Ctot);
+    vo.store_stream(dst + (size_t)p * Ctot);
   };
   int p = p0 + pl;
-  for (; p + 3 * ppi < p1; p += 4 * ppi) {
-    Vec8<T> v[4];
+  for (; p + 7 * ppi < p1; p += 8 * ppi) {   // 8 independent 16-byte loads in flight per thread
+    Vec8<T> v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u].load(src + (size_t)(p + u * ppi) * cs);
+    for (int u = 0; u < 8; ++u) v[u].load_stream(src + (size_t)(p + u * ppi) * cs);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) body(v[u], p + u * ppi);
+    for (int u = 0; u < 8; ++u) body(v[u], p + u * ppi);
   }
   for (; p < p1; p += ppi) {
     Vec8<T> v;
-    v.load(src + (size_t)p * cs);
+    v.load_stream(src + (size_t)p * cs);
     body(v, p);
   }
 }
