@@ -49,6 +49,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+#ifdef ADVS_ATTN_TRACE
+__device__ long long g_attn_trace[64 * 16];
+#define TR(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < 64) g_attn_trace[j * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TR(slot) do { } while (0)
+#endif
+
 template <int DH>
 struct AttnCfg {
   static constexpr int kv_stages = (DH == 256) ? 1 : 2;
@@ -167,14 +174,19 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {
+          TR(11);
           mbar_wait(&k_full[st_s], ph_s);
           tc_fence_after();
+          TR(12);
           issue_s(j + 1, st_s);
           if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
         }
+        TR(8);
         mbar_wait(p_full, (uint32_t)(j & 1));
+        TR(9);
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
+        TR(10);
         const uint32_t v_addr = smem_u32(smem + Cfg::off_v + st * Cfg::v_bytes);
         const uint32_t d = tmem_base + Cfg::o_col;
         if (elect_one()) {
@@ -209,13 +221,16 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     float m_used = -INFINITY;     // base-2 running max actually subtracted (identical in both partners)
     float l = 0.f;                // this half's share of the row sum
     for (int j = 0; j < nblk; ++j) {
+      if (warp == 2) TR(0);
       mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
+      if (warp == 2) TR(1);
       float s[HB];
 #pragma unroll
       for (int c = 0; c < HB / 32; ++c)
         tmem_ld_32x32b_x32(lane_addr + (uint32_t)((j & 1) * kBK + half * HB + c * 32), reinterpret_cast<uint32_t*>(s) + c * 32);
       tmem_wait_ld();
+      if (warp == 2) TR(2);
       float mx = s[0];
 #pragma unroll
       for (int i = 1; i < HB; ++i) mx = fmaxf(mx, s[i]);
@@ -223,6 +238,7 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       xch[((j & 1) * 2 + half) * 128 + row] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
       mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + row]) * kLog2e;
+      if (warp == 2) TR(3);
       float alpha = 1.f;
       bool grow = mx > m_used + kLazyThreshold;
       if (grow) {
@@ -236,10 +252,12 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         sum += s[i];
       }
       l = fmaf(l, alpha, sum);
+      if (warp == 2) TR(4);
       // previous PV must be done before P is overwritten / O is rescaled
       if (j > 0) {
         mbar_wait(o_done, (uint32_t)((j - 1) & 1));
         tc_fence_after();
+        if (warp == 2) TR(5);
         if (__any_sync(0xffffffffu, grow)) {   // both partners take the same decision (same max); each rescales half of O
 #pragma unroll 1
           for (int c = 0; c < HD / 32; ++c) {
@@ -267,10 +285,12 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         v.w = *reinterpret_cast<uint32_t*>(&h3);
         *reinterpret_cast<uint4*>(p_smem + half * (kBQ * 128) + row * 128 + ((c8 ^ (row & 7)) << 4)) = v;
       }
+      if (warp == 2) TR(6);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (warp == 2) TR(7);
     }
     // ---- output: O / l (row sum = both halves) ----
     asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");   // partner has finished reading the last max
@@ -330,6 +350,12 @@ static int attn_launch(const AttnPlan* plan, cudaStream_t st) {
 }  // namespace advs
 
 using namespace advs;
+
+#ifdef ADVS_ATTN_TRACE
+extern "C" int advs_debug_attn_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" {
 
