@@ -23,9 +23,15 @@ def _st():
 
 class ShadowSampler:
     def __init__(self, model: UNetModelBase, diffusion, batch_size, image_size, ddim_timesteps=50,
-                 ddim_discr_method="uniform", clip_denoised=True, precision=None, mask_channels=1, use_graph=True):
+                 ddim_discr_method="uniform", clip_denoised=True, precision=None, mask_channels=1, use_graph=True,
+                 streams=1, _instance=0, _buffers=None):
+        """`streams` > 1 splits the batch into that many independent sub-batches, each with its own engine and
+        CUDA stream: the HBM-bound kernels of one sub-batch (GroupNorm apply, stem, ...) then overlap with the
+        tensor-bound kernels of the other on the same SMs (they need no shared memory, the conv CTAs need it all)."""
         if not isinstance(model, UNetModelBase):
             raise TypeError("ShadowSampler needs an advshadow_b200 UNetModel")
+        if streams > 1 and (batch_size % streams or batch_size // streams < 1):
+            raise ValueError("batch_size must be a multiple of streams")
         self.model, self.gd = model, diffusion
         self.B, self.S, self.n = batch_size, image_size, ddim_timesteps
         self.clip = 1 if clip_denoised else 0
@@ -33,20 +39,49 @@ class ShadowSampler:
         if self.device.type != "cuda":
             raise RuntimeError("ShadowSampler runs on CUDA only (no CPU path)")
         self.C = model.in_channels
+        self.children = []
+        if streams > 1:
+            with torch.cuda.device(self.device):
+                shape = (batch_size, self.C, image_size, image_size)
+                self.x_T = torch.zeros(shape, dtype=torch.float32, device=self.device)
+                self.clean = torch.zeros(shape, dtype=torch.float32, device=self.device)
+                self.fmask = torch.zeros(batch_size, mask_channels, image_size, image_size, dtype=torch.float32,
+                                         device=self.device)
+                self.centers = torch.zeros(batch_size, 2, dtype=torch.float32, device=self.device)
+                self.radii = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
+                self.out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+                sub = batch_size // streams
+                self.side = [torch.cuda.Stream(device=self.device) for _ in range(streams)]
+                for i in range(streams):
+                    sl = slice(i * sub, (i + 1) * sub)
+                    bufs = dict(clean=self.clean[sl], fmask=self.fmask[sl], centers=self.centers[sl], radii=self.radii[sl],
+                                out=self.out[sl])
+                    with torch.cuda.stream(self.side[i]):
+                        self.children.append(ShadowSampler(model, diffusion, sub, image_size, ddim_timesteps,
+                                                           ddim_discr_method, clip_denoised, precision, mask_channels,
+                                                           use_graph, streams=1, _instance=i + 1, _buffers=bufs))
+                torch.cuda.synchronize(self.device)
+            self.eng = self.children[0].eng
+            self.launches_per_trajectory = sum(c.launches_per_trajectory for c in self.children)
+            return
         with torch.cuda.device(self.device):
-            self.eng = model.engine(batch_size, image_size, image_size, precision=precision)
+            self.eng = model.engine(batch_size, image_size, image_size, precision=precision, instance=_instance)
             seq, prev = ddim_timestep_tables(diffusion.timesteps, ddim_timesteps, ddim_discr_method)
             self.coef = diffusion.ddim_coefficients(seq, prev, ddim_timesteps, 0.0).to(self.device)
             ts = torch.tensor([int(seq[i]) for i in reversed(range(ddim_timesteps))], dtype=torch.int64)
             self.table = self.eng.temb_table(ts)
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             shape = (batch_size, self.C, image_size, image_size)
-            self.clean = torch.zeros(shape, dtype=torch.float32, device=self.device)
-            self.fmask = torch.zeros(batch_size, mask_channels, image_size, image_size, dtype=torch.float32,
-                                     device=self.device)
-            self.centers = torch.zeros(batch_size, 2, dtype=torch.float32, device=self.device)
-            self.radii = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
-            self.out = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            if _buffers is not None:      # views into the parent's batch buffers (multi-stream mode)
+                self.clean, self.fmask, self.centers, self.radii, self.out = (_buffers[k] for k in (
+                    "clean", "fmask", "centers", "radii", "out"))
+            else:
+                self.clean = torch.zeros(shape, dtype=torch.float32, device=self.device)
+                self.fmask = torch.zeros(batch_size, mask_channels, image_size, image_size, dtype=torch.float32,
+                                         device=self.device)
+                self.centers = torch.zeros(batch_size, 2, dtype=torch.float32, device=self.device)
+                self.radii = torch.zeros(batch_size, dtype=torch.float32, device=self.device)
+                self.out = torch.zeros(shape, dtype=torch.float32, device=self.device)
             self.n_elems = int(np.prod(shape))
             self.graph = None
             if use_graph:
@@ -75,8 +110,26 @@ class ShadowSampler:
             self._one_step()
         self.step_dev.zero_()
 
+    def load_x_T(self, x_T):
+        """Copy the start noise (device tensor) into the engine state(s)."""
+        if self.children:
+            sub = self.B // len(self.children)
+            for i, c in enumerate(self.children):
+                c.eng.x.copy_(x_T[i * sub:(i + 1) * sub], non_blocking=True)
+        else:
+            self.eng.x.copy_(x_T, non_blocking=True)
+
     def run_device(self):
-        """Trajectory + composite on buffers already resident in HBM (eng.x holds x_T on entry)."""
+        """Trajectory + composite on buffers already resident in HBM (engine state holds x_T on entry)."""
+        if self.children:
+            main = torch.cuda.current_stream()
+            for st, c in zip(self.side, self.children):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    c.run_device()
+            for st in self.side:
+                main.wait_stream(st)
+            return self.out
         self.step_dev.zero_()
         for _ in range(self.n):
             if self.graph is not None:
@@ -90,7 +143,11 @@ class ShadowSampler:
 
     def set_inputs(self, x_T, clean, fmask, centers, radii, non_blocking=True):
         """Copy one batch (host or device tensors) into the static buffers."""
-        self.eng.x.copy_(x_T, non_blocking=non_blocking)
+        if self.children:
+            self.x_T.copy_(x_T, non_blocking=non_blocking)
+            self.load_x_T(self.x_T)
+        else:
+            self.eng.x.copy_(x_T, non_blocking=non_blocking)
         self.clean.copy_(clean, non_blocking=non_blocking)
         self.fmask.copy_(fmask, non_blocking=non_blocking)
         self.centers.copy_(centers, non_blocking=non_blocking)

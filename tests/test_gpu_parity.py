@@ -328,3 +328,20 @@ def test_attack_decisions_agree_with_reference_sampler(pkg):
     assert pred_ref.unique().numel() >= 4 and 0 < int(flags_ref.sum()) < B, "degenerate victim: the check would be vacuous"
     assert agree >= 0.99 and same_class >= 0.99
     model.release_engines()
+
+
+def test_shadow_sampler_multi_stream_matches_single_stream(pkg):
+    """ShadowSampler(streams=2) runs two half-batches on two CUDA streams (HBM-bound kernels of one overlap the
+    tensor-bound kernels of the other); images are independent trajectories, so results must agree."""
+    from advshadow_b200.sampler import ShadowSampler
+    model, _ = get_model(pkg, "dm1")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    B, S, n = 4, 32, 6
+    g = torch.Generator().manual_seed(2)
+    args = (torch.randn(B, 3, S, S, generator=g), torch.rand(B, 3, S, S, generator=g), torch.ones(B, 1, S, S),
+            torch.full((B, 2), S / 2.0), torch.tensor([5.0, 8.0, 11.0, 14.0]))
+    one = ShadowSampler(model, gd, B, S, ddim_timesteps=n)(*args).clone()
+    two = ShadowSampler(model, gd, B, S, ddim_timesteps=n, streams=2)(*args).clone()
+    assert (one - two).abs().max().item() < 5e-2      # bf16 runs with different reduction tiling; same images
+    assert (one - two).abs().mean().item() < 2e-3
+    model.release_engines()
