@@ -189,19 +189,38 @@ class GaussianDiffusionBase:
 
                 graph = None
                 if self.use_cuda_graph and not needs_noise and not keep_all and n > 1:
-                    # one eager step on a side stream first (lazy one-time attribute setup), then capture
-                    s = torch.cuda.Stream(device=device)
-                    s.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(s):
-                        one_step(None)
-                    torch.cuda.current_stream().wait_stream(s)
-                    x.copy_(x_T)
+                    # One captured step per (engine, update kind, clip): every per-call quantity (embedding table,
+                    # coefficient table, step counter) lives in a persistent device buffer the graph reads, so later
+                    # calls with other schedules / step counts only refill the buffers and replay.
+                    cache = eng.__dict__.setdefault("_step_graphs", {})
+                    gkey = (kind, bool(clip_denoised))
+                    st8 = cache.get(gkey)
+                    if st8 is None or st8["cap"] < n:
+                        cap = max(n, 64)
+                        st8 = dict(cap=cap, table=torch.zeros(cap, total, dtype=torch.float32, device=device),
+                                   coef=torch.zeros(cap, 8, dtype=torch.float32, device=device),
+                                   step=torch.zeros(1, dtype=torch.int32, device=device), graph=None)
+                        cache[gkey] = st8
+                    st8["table"][:n].copy_(table)
+                    st8["coef"][:n].copy_(coef_d)
+                    table, coef_d, step_dev = st8["table"], st8["coef"], st8["step"]
                     step_dev.zero_()
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        one_step(None)
-                    x.copy_(x_T)
-                    step_dev.zero_()
+                    if st8["graph"] is None:
+                        # one eager step on a side stream first (lazy one-time attribute setup), then capture
+                        s = torch.cuda.Stream(device=device)
+                        s.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(s):
+                            one_step(None)
+                        torch.cuda.current_stream().wait_stream(s)
+                        x.copy_(x_T)
+                        step_dev.zero_()
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            one_step(None)
+                        st8["graph"] = g
+                        x.copy_(x_T)
+                        step_dev.zero_()
+                    graph = st8["graph"]
                 for i in tqdm(range(n), desc=desc, total=n, disable=None):
                     if graph is not None:
                         graph.replay()

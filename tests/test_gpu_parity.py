@@ -345,3 +345,51 @@ def test_shadow_sampler_multi_stream_matches_single_stream(pkg):
     assert (one - two).abs().max().item() < 5e-2      # bf16 runs with different reduction tiling; same images
     assert (one - two).abs().mean().item() < 2e-3
     model.release_engines()
+
+
+def test_ddim_sample_graph_reuse_across_calls(pkg):
+    """The captured per-step graph is cached on the engine; later calls with another step count / schedule
+    only refill the device tables.  Graph replays must equal eager launches bit for bit."""
+    model, _ = get_model(pkg, "dm1")
+    model.set_precision("bf16")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    torch.manual_seed(0)
+    xT = torch.randn(2, 3, 32, 32)
+    outs = {}
+    for n, method in ((6, "uniform"), (4, "quad"), (6, "uniform")):
+        gd.use_cuda_graph = True
+        a = gd.ddim_sample(model, 32, batch_size=2, channels=3, ddim_timesteps=n, ddim_discr_method=method, x_T=xT)
+        gd.use_cuda_graph = False
+        b = gd.ddim_sample(model, 32, batch_size=2, channels=3, ddim_timesteps=n, ddim_discr_method=method, x_T=xT)
+        assert np.array_equal(a, b), (n, method)
+        outs.setdefault((n, method), a)
+        assert np.array_equal(outs[(n, method)], a)
+    gd.use_cuda_graph = True
+    model.release_engines()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(model_channels=64, channel_mult=(1, 2), attention_resolutions=(2,), num_heads=2, num_res_blocks=1, H=32, W=48),
+    dict(model_channels=32, channel_mult=(1, 2, 2), attention_resolutions=(1, 4), num_heads=4, num_res_blocks=2, H=24, W=24),
+])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_custom_unet_configs_vs_oracle_port(pkg, cfg, precision, tol):
+    """Non-default UNet shapes (non-square input, channel counts that force the SIMT kernels in bf16 mode,
+    attention at full resolution) against the CPU oracle port with the same seeded weights."""
+    from oracle import torch_port as P
+    cfg = dict(cfg)
+    H, W = cfg.pop("H"), cfg.pop("W")
+    torch.manual_seed(0)
+    m = pkg["dm1"].UNetModel(**cfg).eval()
+    params = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    x, t = torch.randn(2, 3, H, W, generator=g), torch.tensor([999, 3])
+    with torch.no_grad():
+        ref = P.unet_forward(params, dict(model_channels=cfg["model_channels"], num_res_blocks=cfg["num_res_blocks"],
+                                          attention_resolutions=cfg["attention_resolutions"], channel_mult=cfg["channel_mult"],
+                                          num_heads=cfg["num_heads"]), x, t)
+    m = m.cuda().set_precision(precision)
+    eps = m(x.cuda(), t.cuda()).cpu()
+    err = (eps - ref).abs().max().item()
+    print(f"custom UNet {cfg} {H}x{W} {precision}: max|eps err| = {err:.3e} (|eps|max {ref.abs().max():.2f})")
+    assert err <= tol
