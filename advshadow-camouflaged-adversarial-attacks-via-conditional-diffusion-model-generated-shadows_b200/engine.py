@@ -52,9 +52,9 @@ class UNetEngine:
         # Upsample + conv3x3 as four low-res 2x2 phase convs (tcgen05 path only; fp32 mode keeps the
         # reference's op order: nearest upsample, then the 3x3 conv)
         fuse_up = conv_impl == "sm100" and spec.model_channels % 64 == 0 and fuse_upsample
-        plan = build_unet_plan(spec, B, H, W, attn_scores_ws=False, fuse_upsample=fuse_up)
-        if any(not self._attn_sm100_ok(op.args) for op in plan.ops if op.kind == "attn"):
-            plan = build_unet_plan(spec, B, H, W, attn_scores_ws=True, fuse_upsample=fuse_up)
+        # only the attention blocks the tcgen05 kernel cannot take get the [B*heads, T, T] SIMT score buffer
+        plan = build_unet_plan(spec, B, H, W, fuse_upsample=fuse_up,
+                               attn_scores_ws=lambda T, dh: not self._attn_sm100_ok(dict(T=T, dh=dh)))
         self.plan: Plan = plan
         for b in plan.bufs.values():
             if b.shape and b.shape[0] == "gn_ws":

@@ -149,7 +149,8 @@ def _conv_flops(B, H, W, cin, cout, taps):
 def build_unet_plan(spec: UNetSpec, B: int, H: int, W: int, attn_scores_ws: bool = False,
                     fuse_upsample: bool = False) -> Plan:
     """Op list for eps = UNetModel(x, t).  `attn_scores_ws`: reserve the [B*heads, T, T] fp32 score
-    buffer the SIMT attention needs (the tcgen05 flash kernel needs none).  `fuse_upsample`: emit
+    buffer the SIMT attention needs (the tcgen05 flash kernel needs none); a bool, or a predicate (T, dh) -> bool
+    deciding per attention block.  `fuse_upsample`: emit
     Upsample's nearest-2x + conv3x3 (dm1:137-139) as one "upconv" op (four 2x2 phase convolutions on the
     low-res tensor, 2.25x fewer MACs, no upsampled intermediate) instead of "up" + "conv"."""
     nlev = len(spec.channel_mult)
@@ -217,7 +218,7 @@ def build_unet_plan(spec: UNetSpec, B: int, H: int, W: int, attn_scores_ws: bool
         o = p.new_buf("attn_o", (B, h, w, c))
         writes = [o]
         ws = None
-        if attn_scores_ws:
+        if attn_scores_ws(T, dh) if callable(attn_scores_ws) else attn_scores_ws:
             ws = p.new_buf("attn_scores", (B * heads, T, T), "f32")
             writes.append(ws)
         p.emit("attn", [q, k, vt], writes, q=q, k=k, vt=vt, dst=o, ws=ws, B=B, heads=heads, T=T, dh=dh)
