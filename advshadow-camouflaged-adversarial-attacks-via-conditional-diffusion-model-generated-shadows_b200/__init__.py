@@ -5,12 +5,13 @@ Public surface:
   shadow                     batched shadow-mask / compositing kernels
   ops                        tensor-level wrappers of single C-ABI entry points
   attack                     data-parallel attack-loop harness (success flags + ASR counts)
+  datasets                   on-disk formats: image / mask_<name> / image_labels.json / id2label readers, writer
   iddm                       IDDM class-conditional UNet + CFG DDIM sampler (model/networks/unet.py, model/samples/ddim.py)
 The CUDA kernels live in csrc/ and are reached only through the C ABI in include/advshadow_b200.h.
 """
 from . import _capi  # noqa: F401
 
-__all__ = ["diff_model", "diff_model2", "shadow", "ops", "attack", "iddm", "sampler", "plan", "engine"]
+__all__ = ["diff_model", "diff_model2", "shadow", "ops", "attack", "iddm", "datasets", "sampler", "plan", "engine"]
 __version__ = "0.1.0"
 
 

@@ -1,0 +1,87 @@
+"""On-disk formats either side of the sampler: the image / mask / label files the reference's
+scripts read and write.  Host-side I/O only (PIL + JSON); nothing here touches the GPU.
+
+  images/<label>_<n>.<ext>                  true label = text before the LAST '_' (ASR_fast.py:109)
+  masks/mask_<image file name>              single-channel 0/255 PNG feature mask (mask_for_dataset.py:29,76-80)
+  image_labels.json                         {"<file>": "<class name>", ...} (classifer_model.py:36-60, main.py:43-50)
+  config*.json                              {"id2label": {"0": "Abyssinian", ...}} per victim (ASR_fast.py:67-75)
+"""
+import json
+import os
+from typing import Dict, List, Sequence, Tuple
+
+from torch.utils.data import Dataset
+
+from ._compat import Image
+from .attack import label_from_filename, load_id2label  # noqa: F401  (re-exported: same rules)
+
+IMAGE_EXTENSIONS = ('png', 'jpg', 'jpeg', 'bmp', 'gif')      # ASR_fast.py:105
+
+
+def load_image_labels(path: str) -> Tuple[List[str], List[str]]:
+    """image_labels.json -> (files, labels) in file order, as main.py:47-50 unpacks it."""
+    with open(path, 'r') as f:
+        image_labels = json.load(f)
+    files, labels = zip(*[(k, v) for k, v in image_labels.items()]) if image_labels else ((), ())
+    return list(files), list(labels)
+
+
+def list_images(folder: str) -> List[str]:
+    """The files compute_asr walks (ASR_fast.py:104-105), sorted for reproducible sharding."""
+    return sorted(f for f in os.listdir(folder) if f.lower().endswith(IMAGE_EXTENSIONS))
+
+
+def mask_name(image_name: str) -> str:
+    return 'mask_' + image_name                                  # ddim2/main2.py:48, mask_for_dataset.py:29
+
+
+class ImageLabelDataset(Dataset):
+    """main.py:9-29 `CustomDataset`: RGB image + label from parallel lists."""
+
+    def __init__(self, image_dir, image_files: Sequence[str], labels: Sequence, transform=None):
+        self.image_dir, self.image_files, self.labels, self.transform = image_dir, list(image_files), list(labels), transform
+
+    def __len__(self):
+        return len(self.image_files)
+
+    def __getitem__(self, idx):
+        image = Image.open(os.path.join(self.image_dir, self.image_files[idx])).convert('RGB')
+        if self.transform:
+            image = self.transform(image)
+        return image, self.labels[idx]
+
+
+class ImageMaskLabelDataset(Dataset):
+    """ddim2/main2.py:30-66 `CustomDataset`: RGB image, 'L' feature mask `mask_<name>` run through the SAME transform
+    (so a bilinear Resize leaves soft mask edges -- they are not re-binarised), label; unreadable samples are skipped
+    by moving to the next index, like the reference does."""
+
+    def __init__(self, image_dir, mask_dir, image_files: Sequence[str], labels: Sequence, transform=None):
+        self.image_dir, self.mask_dir, self.transform = image_dir, mask_dir, transform
+        self.image_files, self.labels = list(image_files), list(labels)
+
+    def __len__(self):
+        return len(self.image_files)
+
+    def __getitem__(self, idx):
+        for _ in range(len(self.image_files)):
+            try:
+                name = self.image_files[idx]
+                image = Image.open(os.path.join(self.image_dir, name)).convert('RGB')
+                mask = Image.open(os.path.join(self.mask_dir, mask_name(name))).convert('L')
+                if self.transform:
+                    image, mask = self.transform(image), self.transform(mask)
+                return image, mask, self.labels[idx]
+            except (OSError, FileNotFoundError):
+                idx = (idx + 1) % len(self.image_files)
+        raise FileNotFoundError("no readable (image, mask) pair in the dataset")
+
+
+def save_images(images, folder: str, names: Sequence[str]):
+    """Write [N,3,H,W] tensors in [0,1] as PNG/JPG files named like the inputs (`<label>_<n>.<ext>`), the layout
+    compute_asr and classifer_model.py read back."""
+    import numpy as np
+    os.makedirs(folder, exist_ok=True)
+    arr = (images.detach().float().clamp(0, 1).mul(255).round().byte().permute(0, 2, 3, 1).cpu().numpy())
+    for a, n in zip(arr, names):
+        Image.fromarray(np.ascontiguousarray(a)).save(os.path.join(folder, n))

@@ -107,5 +107,41 @@ class GaussianDiffusion(GaussianDiffusionBase):
                 shadow_radius.clamp_(min=0, max=min(original_image.size(1), original_image.size(2)) / 2)
         return shadow_center.detach(), shadow_radius.detach(), shadowed_image
 
+    def optimize_shadow_position_batched(self, classifier, original_images, masks, target_labels, device, lr=1e-1,
+                                         iterations=10, shadow_intensity=0.33, epsilon=0.01):
+        """`optimize_shadow_position` for B images at once -- the reference runs a Python loop with
+        batch-1 victim calls per image (ddim2/main2.py:159-168).  Per image this is exactly the single-image algorithm
+        (Adam is element-wise, the FGSM sign ignores the 1/B of the mean cross-entropy): masks and composites run on
+        the batched GPU kernels, the victim forward/backward is one batched PyTorch call per iteration.
+        original_images [B,C,H,W], masks [B,1|C,H,W], target_labels [B] -> (centers [B,2], radii [B], images [B,C,H,W])."""
+        imgs = original_images.to(device).float()
+        masks = masks.to(device).float()
+        B, Cc, H, W = imgs.shape
+        centers0 = torch.stack([_shadow.mask_center(masks[i]) for i in range(B)]).to(device)
+        centers = torch.nn.Parameter(centers0.clone(), requires_grad=True)
+        radii = torch.nn.Parameter(torch.full((B,), 20.0, device=device), requires_grad=True)
+        optimizer = torch.optim.Adam([centers, radii], lr=lr)
+        victim = classifier.model.to(device)
+        out = None
+        for _ in range(iterations):
+            optimizer.zero_grad()
+            sm = _shadow.disk_mask(centers, radii, H, W)
+            shadowed, _ = _shadow.composite(imgs, sm, masks, shadow_intensity, want_out=False)
+            x = shadowed.detach().clone().requires_grad_(True)          # FGSM step, dm2:572-613
+            with torch.enable_grad():
+                loss_adv = F.cross_entropy(victim(x), target_labels)
+                victim.zero_grad()
+                loss_adv.backward()
+            adv = torch.clamp(x + epsilon * x.grad.data.sign(), 0, 1).detach()
+            _, out = _shadow.composite(imgs, sm, masks, shadow_intensity, adv=adv, want_shadowed=False)
+            # only the regulariser reaches (centre, radius): the hard mask passes no gradient (dm2:503-510)
+            reg = (centers - centers0).pow(2).sum() + radii.pow(2).sum()
+            (0.1 * reg).backward()
+            optimizer.step()
+            with torch.no_grad():
+                centers.clamp_(min=0, max=W)
+                radii.clamp_(min=0, max=min(H, W) / 2)
+        return centers.detach(), radii.detach(), out
+
     def train_losses(self, model, x_start, t, device=None):   # dm2:656-679
         return super().train_losses(model, x_start, t)

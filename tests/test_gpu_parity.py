@@ -393,3 +393,27 @@ def test_custom_unet_configs_vs_oracle_port(pkg, cfg, precision, tol):
     err = (eps - ref).abs().max().item()
     print(f"custom UNet {cfg} {H}x{W} {precision}: max|eps err| = {err:.3e} (|eps|max {ref.abs().max():.2f})")
     assert err <= tol
+
+
+def test_batched_shadow_optimisation_equals_per_image_loop(pkg):
+    """optimize_shadow_position_batched == the reference-shaped single-image method applied to each
+    image (dm2:457-550), with a small PyTorch victim."""
+    gd = pkg["dm2"].GaussianDiffusion()
+    torch.manual_seed(0)
+
+    class Victim:
+        model = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, stride=2, padding=1), torch.nn.ReLU(), torch.nn.Flatten(),
+                                    torch.nn.Linear(8 * 16 * 16, 37)).cuda().eval()
+
+    g = torch.Generator().manual_seed(8)
+    B, S = 3, 32
+    imgs = torch.rand(B, 3, S, S, generator=g).cuda()
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    masks = torch.stack([(((xx - cx) ** 2 + (yy - cy) ** 2) <= 100).float()[None] for cx, cy in ((10, 12), (20, 16), (15, 22))]).cuda()
+    target = torch.tensor([3, 7, 11]).cuda()
+    cb, rb, ob = gd.optimize_shadow_position_batched(Victim, imgs, masks, target, "cuda", iterations=6)
+    for i in range(B):
+        c, r, o = gd.optimize_shadow_position(Victim, imgs[i], masks[i], target[i:i + 1], "cuda", iterations=6)
+        assert torch.allclose(cb[i].cpu(), c.cpu(), atol=1e-5) and abs(float(rb[i]) - float(r)) < 1e-5
+        assert torch.allclose(ob[i], o[0], atol=1e-6)
+    assert float(rb.max()) < 20.0        # Adam on the regulariser shrank the radii, as in the reference
