@@ -20,9 +20,13 @@ struct ConvCfgH {
   static constexpr uint32_t b_bytes = (BN / 2) * 128;          // this CTA's half of one tap's weight tile
   static constexpr uint32_t a_buf_bytes = 49 * 1024;           // >= 3 rows x 130 pixels x 128 B, 1 KB aligned
   static constexpr int a_bufs = 2;                             // (3 buffers + a 5-deep weight ring measured slower)
-  static constexpr int stages = (BN == 256) ? 6 : 10;          // weight-tile ring
+  // BN = 128: an MMA per tap is only 4 x 64 tensor cycles, about what one mbarrier wait + commit costs the
+  // issuing warp, so three taps (one kernel row) share a ring stage and a barrier round trip
+  static constexpr int tps = (BN == 256) ? 1 : 3;              // taps per weight-ring stage
+  static constexpr uint32_t stage_bytes = tps * b_bytes;
+  static constexpr int stages = (BN == 256) ? 6 : 4;           // weight-tile ring
   static constexpr uint32_t off_b = a_bufs * a_buf_bytes;
-  static constexpr uint32_t off_bar = off_b + stages * b_bytes;
+  static constexpr uint32_t off_bar = off_b + stages * stage_bytes;
   static constexpr uint32_t bar_bytes = 512;
   static constexpr uint32_t stat_bytes = 2 * 4 * BN * 8;
   static constexpr uint32_t smem_bytes = off_bar + bar_bytes + stat_bytes + 1024;
@@ -102,10 +106,13 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
             tma_load_4d_2cta(smem + abuf * Cfg::a_buf_bytes, amap, &a_full[abuf], cb * 64, cw, ch, n0);
             if (!leader) mbar_arrive_leader(&a_full[abuf]);
             if (++abuf == Cfg::a_bufs) { abuf = 0; aphase ^= 1; }
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap0 = 0; tap0 < taps; tap0 += Cfg::tps) {
+              const int ng = min(Cfg::tps, taps - tap0);
               mbar_wait(&empty[stage], phase ^ 1);
-              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::b_bytes);
-              tma_load_3d_2cta(smem + Cfg::off_b + stage * Cfg::b_bytes, &maps.b[s], &full[stage], cb * 64, tap, nb);
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * ng * Cfg::b_bytes);
+              for (int g = 0; g < ng; ++g)
+                tma_load_3d_2cta(smem + Cfg::off_b + stage * Cfg::stage_bytes + g * Cfg::b_bytes, &maps.b[s], &full[stage],
+                                 cb * 64, tap0 + g, nb);
               if (!leader) mbar_arrive_leader(&full[stage]);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -131,18 +138,27 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
           for (int cb = 0; cb < a.cblks[s]; ++cb) {
             mbar_wait(&a_full[abuf], aphase);
             const uint32_t a_base = smem_u32(smem + abuf * Cfg::a_buf_bytes);
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap0 = 0; tap0 < taps; tap0 += Cfg::tps) {
+              const int ng = min(Cfg::tps, taps - tap0);
               mbar_wait(&full[stage], phase);
               tc_fence_after();
-              // the tap is a whole-row shift inside the halo box; SWIZZLE_128B is a function of the absolute
-              // shared-memory address, so a row-shifted descriptor reads what TMA wrote (selftest_sm100.cu)
-              const int row_off = taps == 9 ? (tap / 3) * 130 + tap % 3 : (taps == 4 ? (tap >> 1) * 129 + (tap & 1) : 0);
-              const uint64_t adesc = umma_desc_k_sw128(a_base + (uint32_t)row_off * 128u);
-              const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem + Cfg::off_b + stage * Cfg::b_bytes));
+              const uint32_t b_base = smem_u32(smem + Cfg::off_b + stage * Cfg::stage_bytes);
               if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                for (int g = 0; g < Cfg::tps; ++g) {
+                  if (g < ng) {
+                    // the tap is a whole-row shift inside the halo box; SWIZZLE_128B is a function of the absolute
+                    // shared-memory address, so a row-shifted descriptor reads what TMA wrote (selftest_sm100.cu)
+                    const int tap = tap0 + g;
+                    const int row_off = taps == 9 ? (tap / 3) * 130 + tap % 3 : (taps == 4 ? (tap >> 1) * 129 + (tap & 1) : 0);
+                    const uint64_t adesc = umma_desc_k_sw128(a_base + (uint32_t)row_off * 128u);
+                    const uint64_t bdesc = umma_desc_k_sw128(b_base + (uint32_t)g * Cfg::b_bytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                     (first && g == 0 && k == 0) ? 0u : 1u);
+                  }
+                }
                 umma_commit_2cta(&empty[stage], 3);
               }
               __syncwarp();
