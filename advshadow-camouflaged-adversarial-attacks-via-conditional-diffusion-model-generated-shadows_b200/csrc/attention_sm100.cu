@@ -36,16 +36,21 @@ struct AttnPlan {
 };
 static_assert(sizeof(AttnPlan) <= ADVS_ATTN_PLAN_BYTES, "AttnPlan does not fit ADVS_ATTN_PLAN_BYTES");
 
-constexpr int kAttnThreads = 320;   // TMA warp + MMA warp + 8 softmax warps
+// Three warpgroups: {TMA warp, MMA warp, two idle warps} + 8 softmax warps.  Registers are allocated to warps
+// in groups of four, so 12 warps start at 168 registers each; the first group hands most of its share to
+// the softmax groups (setmaxnreg), which keep two blocks of scores in registers.
+constexpr int kAttnThreads = 384;
+constexpr int kAttnFirstSoftmaxWarp = 4;
 constexpr int kBQ = 128;   // queries per CTA
 constexpr int kBK = 128;   // keys per block
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLazyThreshold = 8.0f;  // rescale O only if the row max grew by > 2^8
 // (ex2.approx.ftz.bf16x2 was tried to halve the MUFU load: ptxas splits it into two MUFU.EX2.BF16 ops on
 //  sm_100a, so it buys nothing and costs accuracy -- scores keep the fp32 ex2.)
-__device__ __forceinline__ float fast_exp2(float x) {
+// volatile: the softmax loop places its exponentials by hand between barrier waits (see below)
+__device__ __forceinline__ float ex2_pinned(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -67,7 +72,13 @@ struct AttnCfg {
   static constexpr uint32_t off_k = off_q + q_bytes;
   static constexpr uint32_t off_v = off_k + kv_stages * k_bytes;
   static constexpr uint32_t off_p = off_v + kv_stages * v_bytes;
-  static constexpr uint32_t off_bar = off_p + p_bytes;
+  // dh <= 128: P lives in tensor memory (two tiles of 64 columns next to S0 | S1 | O) and is the PV MMA's A
+  // operand from there -- no shared-memory round trip, and PV only streams V.  dh = 256 fills TMEM with
+  // S and O, so its P goes through one swizzled shared-memory tile.
+  static constexpr bool p_in_tmem = DH <= 128;
+  static constexpr int p_bufs = p_in_tmem ? 2 : 1;
+  static constexpr uint32_t off_bar = off_p + (p_in_tmem ? 0 : p_bytes);
+  static constexpr uint32_t p_col = 384;
   static constexpr uint32_t smem_bytes = off_bar + 128 + 2048 + 896;   // barriers + max/sum exchange + alignment slack (base is 128-B aligned)
   static constexpr uint32_t tmem_cols = 512;
   static constexpr uint32_t o_col = 256;
@@ -88,8 +99,8 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   uint64_t* v_empty = bars + 7;       // KVS
   uint64_t* s_full = bars + 9;        // 2
   uint64_t* p_full = bars + 11;       // 1
-  uint64_t* o_done = bars + 12;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* o_done = bars + 12;       // 2: PV of even / odd blocks (a waiter may then lag two blocks behind)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
@@ -110,7 +121,8 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     mbar_init(p_full, 8);
-    mbar_init(o_done, 1);
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::tmem_cols>(tmem_slot);
@@ -119,12 +131,15 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < kAttnFirstSoftmaxWarp) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, Cfg::q_bytes);
       for (int sl = 0; sl < DH / 64; ++sl)
         tma_load_2d(smem + Cfg::off_q + sl * (kBQ * 128), &maps.q, q_full, sl * 64, bh * a.T + q_tile * kBQ);
+      // keys: stage st is free again as soon as S_j has drained
       int st = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nblk; ++j) {
@@ -133,6 +148,17 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         for (int sl = 0; sl < DH / 64; ++sl)
           tma_load_2d(smem + Cfg::off_k + st * Cfg::k_bytes + sl * (kBK * 128), &maps.k, &k_full[st], sl * 64,
                       bh * a.T + j * kBK);
+        if (++st == KVS) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= TMA producer for V^T (its own warp: a V stage is released by PV_j, much later than the
+    // K stage of the same block, and one thread issuing both in order would hold the next S behind it) ====
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.vt);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], Cfg::v_bytes);
         for (int sl = 0; sl < kBK / 64; ++sl)
@@ -163,6 +189,27 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
         }
         __syncwarp();
       };
+      // PV of block j, then release the V stage and tell the softmax warps P / O may be touched again
+      auto issue_pv = [&](int j, int st) {
+        const uint32_t v_addr = smem_u32(smem + Cfg::off_v + st * Cfg::v_bytes);
+        const uint32_t d = tmem_base + Cfg::o_col;
+        const uint32_t p_tmem = tmem_base + Cfg::p_col + (uint32_t)(j & 1) * (kBK / 2);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint32_t offp = (uint32_t)(k >> 2) * (kBQ * 128) + (uint32_t)(k & 3) * 32;
+            const uint32_t offv = (uint32_t)(k >> 2) * (DH * 128) + (uint32_t)(k & 3) * 32;
+            if (Cfg::p_in_tmem)
+              umma_bf16_ts(d, p_tmem + (uint32_t)k * 8, umma_desc_k_sw128(v_addr + offv), idesc_o, (j | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(d, umma_desc_k_sw128(p_addr + offp), umma_desc_k_sw128(v_addr + offv), idesc_o,
+                        (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_done[j & 1]);
+          umma_commit(&v_empty[st]);
+        }
+        __syncwarp();
+      };
       int st = 0;       // stage of block j (the PV side)
       uint32_t ph = 0;
       int st_s = 0;     // stage of the S being issued
@@ -172,46 +219,62 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       tc_fence_after();
       issue_s(0, 0);
       if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          TR(11);
+      if (KVS >= 2) {
+        // Two key stages: S runs TWO blocks ahead.  When the softmax warps hand over P_j they have long since
+        // read S_{j+1} into registers, so S_{j+2} is issued first and PV_j second: S_{j+2} is complete by the
+        // middle of the exponentials of block j+1, whose shadow then hides the max / exchange of block j+2.
+        if (nblk > 1) {
           mbar_wait(&k_full[st_s], ph_s);
           tc_fence_after();
-          TR(12);
-          issue_s(j + 1, st_s);
+          issue_s(1, st_s);
           if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
         }
-        TR(8);
-        mbar_wait(p_full, (uint32_t)(j & 1));
-        TR(9);
-        mbar_wait(&v_full[st], ph);
-        tc_fence_after();
-        TR(10);
-        const uint32_t v_addr = smem_u32(smem + Cfg::off_v + st * Cfg::v_bytes);
-        const uint32_t d = tmem_base + Cfg::o_col;
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint32_t offp = (uint32_t)(k >> 2) * (kBQ * 128) + (uint32_t)(k & 3) * 32;
-            const uint32_t offv = (uint32_t)(k >> 2) * (DH * 128) + (uint32_t)(k & 3) * 32;
-            umma_bf16(d, umma_desc_k_sw128(p_addr + offp), umma_desc_k_sw128(v_addr + offv), idesc_o,
-                      (j | k) != 0 ? 1u : 0u);
+        for (int j = 0; j < nblk; ++j) {
+          TR(8);
+          mbar_wait(p_full, (uint32_t)(j & 1));
+          TR(9);
+          if (j + 2 < nblk) {
+            mbar_wait(&k_full[st_s], ph_s);
+            tc_fence_after();
+            TR(11);
+            issue_s(j + 2, st_s);
+            TR(12);
+            if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
           }
-          umma_commit(o_done);
-          umma_commit(&v_empty[st]);
+          mbar_wait(&v_full[st], ph);
+          tc_fence_after();
+          TR(10);
+          issue_pv(j, st);
+          TR(13);
+          if (++st == KVS) { st = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++st == KVS) { st = 0; ph ^= 1; }
+      } else {
+        // one key stage (dh = 256): S one block ahead
+        for (int j = 0; j < nblk; ++j) {
+          if (j + 1 < nblk) {
+            mbar_wait(&k_full[st_s], ph_s);
+            tc_fence_after();
+            issue_s(j + 1, st_s);
+            if (++st_s == KVS) { st_s = 0; ph_s ^= 1; }
+          }
+          mbar_wait(p_full, (uint32_t)(j & 1));
+          mbar_wait(&v_full[st], ph);
+          tc_fence_after();
+          issue_pv(j, st);
+          if (++st == KVS) { st = 0; ph ^= 1; }
+        }
       }
     }
+  }
   } else {
-    // ================= softmax / correction / output (warps 2..9) =================
-    // Two warps per TMEM lane quarter: warps 2-5 own keys [0,64) of each block, warps 6-9 keys [64,128).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ================= softmax / correction / output (warps 4..11) =================
+    // Two warps per TMEM lane quarter: warps 4-7 own keys [0,64) of each block, warps 8-11 keys [64,128).
     // The softmax is MUFU-bound (one ex2 per score); two warps per scheduler let one warp's TMEM loads,
     // smem stores and barrier waits hide behind the other's exponentials.  The row maximum is exchanged
     // through shared memory once per block; the row sums are combined once at the end.
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - kAttnFirstSoftmaxWarp) >> 2;
     const int row = qd * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(qd * 32) << 16);
     uint8_t* p_smem = smem + Cfg::off_p;
@@ -220,44 +283,113 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     constexpr int HD = DH / 2;    // O columns per warp (rescale / output)
     float m_used = -INFINITY;     // base-2 running max actually subtracted (identical in both partners)
     float l = 0.f;                // this half's share of the row sum
-    for (int j = 0; j < nblk; ++j) {
-      if (warp == 2) TR(0);
-      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      if (warp == 2) TR(1);
-      float s[HB];
+    // The loop is software-pipelined by hand around the MUFU pipe (16 ex2 / clk / SM is the softmax bound; the
+    // two warps of a row pair share a scheduler and run in lockstep, so nothing else hides their latencies):
+    // the 64 exponentials of block j are issued in four groups, and between the groups the warp fetches S_{j+1}
+    // from TMEM, takes its row maximum and exchanges it with the partner.  All pieces are volatile asm so
+    // ptxas keeps this order.
+    float sa[HB], sb[HB];
+    auto ld_scores = [&](int j, float* dst) {
 #pragma unroll
       for (int c = 0; c < HB / 32; ++c)
-        tmem_ld_32x32b_x32(lane_addr + (uint32_t)((j & 1) * kBK + half * HB + c * 32), reinterpret_cast<uint32_t*>(s) + c * 32);
-      tmem_wait_ld();
-      if (warp == 2) TR(2);
-      float mx = s[0];
+        tmem_ld_32x32b_x32(lane_addr + (uint32_t)((j & 1) * kBK + half * HB + c * 32), reinterpret_cast<uint32_t*>(dst) + c * 32);
+    };
+    auto half_max = [&](const float* v) {
+      float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-      for (int i = 1; i < HB; ++i) mx = fmaxf(mx, s[i]);
-      // exchange the half-row maxima with the partner warp (same rows, other 64 keys)
-      xch[((j & 1) * 2 + half) * 128 + row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
-      mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + row]) * kLog2e;
-      if (warp == 2) TR(3);
+      for (int i = 4; i < HB; i += 4) {
+        m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+      }
+      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    };
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    ld_scores(0, sa);
+    tmem_wait_ld();
+    float mx = half_max(sa);
+    xch[half * 128 + row] = mx;
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
+    mx = fmaxf(mx, xch[(half ^ 1) * 128 + row]) * kLog2e;
+    auto block = [&](const int j, float* __restrict__ s, float* __restrict__ sn) {
+      const bool more = j + 1 < nblk;
+      constexpr int PB = Cfg::p_bufs;
+      if (warp == kAttnFirstSoftmaxWarp) TR(0);
       float alpha = 1.f;
-      bool grow = mx > m_used + kLazyThreshold;
+      const bool grow = mx > m_used + kLazyThreshold;
       if (grow) {
         alpha = exp2f(m_used - mx);  // 0 on the first block (m_used = -inf)
         m_used = mx;
       }
-      float sum = 0.f;
+      // P -> bf16.  Tensor-memory P: this thread's row, 32-bit column = two keys; the pieces go out as soon
+      // as they are packed (the tile's previous reader is PV_{j-2}, long done).  Shared-memory P (dh = 256):
+      // K-major SWIZZLE_128B slab `half` of [128 rows][64 keys], written after PV_{j-1} has drained.
+      uint8_t* p_row = p_smem + half * (kBQ * 128) + row * 128;
+      const uint32_t p_taddr = lane_addr + Cfg::p_col + (uint32_t)((j & 1) * (kBK / 2) + half * (HB / 2));
+      auto p_store = [&](int c8, const uint32_t* w) {   // c8: group of 8 keys = 4 packed words
+        *reinterpret_cast<uint4*>(p_row + ((c8 ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      };
+      auto p_store16 = [&](int g, const uint32_t* w) {  // g: group of 16 keys = 8 packed words
+        if (PB == 2) tmem_st_32x32b_x8(p_taddr + (uint32_t)g * 8, w);
+      };
+      if (PB == 2 && j >= 2) mbar_wait(&o_done[j & 1], (uint32_t)(((j - 2) >> 1) & 1));
+      // Four groups of 16 exponentials.  The two warps of a row pair share a scheduler and run in lockstep, so
+      // the MUFU pipe is only kept busy if every exponential is followed by its share of the other work
+      // (row sum and bf16 packing of the previous group, the row maximum of the next block): written
+      // interleaved here, one slice per ex2.
+      constexpr int G = HB / 4;
+      uint32_t pk[HB / 2];
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < HB; ++i) {
-        s[i] = fast_exp2(fmaf(s[i], kLog2e, -m_used));
-        sum += s[i];
+      for (int i = 0; i < G; ++i) s[i] = ex2_pinned(fmaf(s[i], kLog2e, -m_used));
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        s[G + i] = ex2_pinned(fmaf(s[G + i], kLog2e, -m_used));
+        if (i & 1) { (i & 2 ? sum3 : sum1) += s[i]; pk[i >> 1] = pack_bf16x2(s[i - 1], s[i]); } else (i & 2 ? sum2 : sum0) += s[i];
       }
-      l = fmaf(l, alpha, sum);
-      if (warp == 2) TR(4);
-      // previous PV must be done before P is overwritten / O is rescaled
-      if (j > 0) {
-        mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+      p_store16(0, pk);
+      if (warp == kAttnFirstSoftmaxWarp) TR(1);
+      if (more) {      // S_{j+1} was issued when P_{j-1} was handed over: complete about now
+        mbar_wait(&s_full[(j + 1) & 1], (uint32_t)(((j + 1) >> 1) & 1));
         tc_fence_after();
-        if (warp == 2) TR(5);
+        ld_scores(j + 1, sn);
+      }
+      if (warp == kAttnFirstSoftmaxWarp) TR(2);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        s[2 * G + i] = ex2_pinned(fmaf(s[2 * G + i], kLog2e, -m_used));
+        if (i & 1) { (i & 2 ? sum3 : sum1) += s[G + i]; pk[(G + i) >> 1] = pack_bf16x2(s[G + i - 1], s[G + i]); } else (i & 2 ? sum2 : sum0) += s[G + i];
+      }
+      p_store16(1, pk + 8);
+      if (more) tmem_wait_ld();
+      if (warp == kAttnFirstSoftmaxWarp) TR(3);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        s[3 * G + i] = ex2_pinned(fmaf(s[3 * G + i], kLog2e, -m_used));
+        if (i & 1) { (i & 2 ? sum3 : sum1) += s[2 * G + i]; pk[(2 * G + i) >> 1] = pack_bf16x2(s[2 * G + i - 1], s[2 * G + i]); } else (i & 2 ? sum2 : sum0) += s[2 * G + i];
+        if (more) {
+          m0 = fmaxf(m0, sn[4 * i]); m1 = fmaxf(m1, sn[4 * i + 1]); m2 = fmaxf(m2, sn[4 * i + 2]); m3 = fmaxf(m3, sn[4 * i + 3]);
+        }
+      }
+      float mxn = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      if (more) xch[(((j + 1) & 1) * 2 + half) * 128 + row] = mxn;
+      p_store16(2, pk + 16);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        if (i & 1) { (i & 2 ? sum3 : sum1) += s[3 * G + i]; pk[(3 * G + i) >> 1] = pack_bf16x2(s[3 * G + i - 1], s[3 * G + i]); } else (i & 2 ? sum2 : sum0) += s[3 * G + i];
+      }
+      p_store16(3, pk + 24);
+      if (more) {
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
+        mxn = fmaxf(mxn, xch[(((j + 1) & 1) * 2 + (half ^ 1)) * 128 + row]) * kLog2e;
+      }
+      l = fmaf(l, alpha, (sum0 + sum1) + (sum2 + sum3));
+      if (warp == kAttnFirstSoftmaxWarp) TR(4);
+      // PV_{j-1} must be done before O is rescaled (and, with one P tile, before P is overwritten)
+      if (j > 0 && (PB == 1 || __any_sync(0xffffffffu, grow))) {
+        mbar_wait(&o_done[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));
+        tc_fence_after();
+        if (warp == kAttnFirstSoftmaxWarp) TR(5);
         if (__any_sync(0xffffffffu, grow)) {   // both partners take the same decision (same max); each rescales half of O
 #pragma unroll 1
           for (int c = 0; c < HD / 32; ++c) {
@@ -271,33 +403,30 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
           tmem_wait_st();
         }
       }
-      // P -> bf16 -> smem, K-major SWIZZLE_128B: slab `half` of [128 rows][64 keys]
+      if (PB == 1) {
 #pragma unroll
-      for (int c8 = 0; c8 < HB / 8; ++c8) {
-        uint4 v;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(s[c8 * 8 + 0], s[c8 * 8 + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(s[c8 * 8 + 2], s[c8 * 8 + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(s[c8 * 8 + 4], s[c8 * 8 + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(s[c8 * 8 + 6], s[c8 * 8 + 7]);
-        v.x = *reinterpret_cast<uint32_t*>(&h0);
-        v.y = *reinterpret_cast<uint32_t*>(&h1);
-        v.z = *reinterpret_cast<uint32_t*>(&h2);
-        v.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(p_smem + half * (kBQ * 128) + row * 128 + ((c8 ^ (row & 7)) << 4)) = v;
+        for (int c8 = 0; c8 < HB / 8; ++c8) p_store(c8, pk + 4 * c8);
       }
-      if (warp == 2) TR(6);
-      fence_proxy_async_smem();
+      if (warp == kAttnFirstSoftmaxWarp) TR(6);
+      if (PB == 2) tmem_wait_st();
+      else fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      if (warp == 2) TR(7);
+      if (warp == kAttnFirstSoftmaxWarp) TR(7);
+      mx = mxn;
+    };
+    // two blocks per trip so the score registers of block j+1 become "current" without being copied
+    for (int j = 0; j < nblk; j += 2) {
+      block(j, sa, sb);
+      if (j + 1 < nblk) block(j + 1, sb, sa);
     }
     // ---- output: O / l (row sum = both halves) ----
     asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");   // partner has finished reading the last max
     xch[half * 128 + row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
     l += xch[(half ^ 1) * 128 + row];
-    mbar_wait(o_done, (uint32_t)((nblk - 1) & 1));
+    mbar_wait(&o_done[(nblk - 1) & 1], (uint32_t)(((nblk - 1) >> 1) & 1));
     tc_fence_after();
     const float inv = 1.f / l;
     const int b = bh / a.heads, head = bh - b * a.heads;

@@ -146,4 +146,9 @@ inline EpilogueParams make_epilogue(const advs_conv_params& p) {
 
 int validate_conv(const advs_conv_params* p, const char* who);
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 }  // namespace advs

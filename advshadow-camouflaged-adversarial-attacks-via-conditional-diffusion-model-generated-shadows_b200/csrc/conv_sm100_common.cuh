@@ -53,11 +53,6 @@ struct ConvCfg {
   static constexpr uint32_t tmem_cols = 2 * BN;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
 // 32 consecutive output channels [n, n+32) of one pixel row: v = acc + bias + temb + residual
 __device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, const uint32_t* acc, float* v, size_t m,
                                                    int b, int n) {

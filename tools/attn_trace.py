@@ -22,13 +22,14 @@ buf = (C.c_longlong * (64 * 16))()
 lib.advs_debug_attn_trace.restype = C.c_int
 assert lib.advs_debug_attn_trace(buf) == 0
 tr = [[buf[j * 16 + s] for s in range(16)] for j in range(64)]
-names = ["sm:wait_S", "sm:ldtm", "sm:max+xchg", "sm:exp", "sm:wait_o_done", "sm:P_store", "sm:fence+arrive"]
-print("softmax warp 2, cycles per phase (blocks 8..15); last column = block period")
+names = ["ex2 g0,g1", "wait S(j+1) + ldtm issue", "ex2 g2 + ldtm wait", "ex2 g3 + max + sums + exchange", "(rescale) + P tail", "fence + arrive"]
+print("first softmax warp, cycles per phase (blocks 8..15); last column = block period")
 for j in range(8, 16):
     t = tr[j]
-    ph = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]]
+    ph = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[6] - t[4], t[7] - t[6]]
     print(j, dict(zip(names, ph)), "period", tr[j + 1][0] - t[0])
-print("MMA warp: wait_P, wait_V, [issue PV], gap to next S wait, wait_K")
+print("MMA warp (two key stages)")
 for j in range(8, 16):
     t = tr[j]
-    print(j, {"top->waitP_done": t[9] - t[8], "waitV": t[10] - t[9], "iter_period": tr[j + 1][8] - t[8], "waitK": t[12] - t[11]})
+    print(j, {"wait_P": t[9] - t[8], "wait_K": t[11] - t[9], "issue_S": t[12] - t[11], "wait_V": t[10] - t[12], "issue_PV": t[13] - t[10],
+              "iter_period": tr[j + 1][8] - t[8]})
