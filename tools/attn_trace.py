@@ -22,14 +22,14 @@ buf = (C.c_longlong * (64 * 16))()
 lib.advs_debug_attn_trace.restype = C.c_int
 assert lib.advs_debug_attn_trace(buf) == 0
 tr = [[buf[j * 16 + s] for s in range(16)] for j in range(64)]
-names = ["ex2 g0,g1", "wait S(j+1) + ldtm issue", "ex2 g2 + ldtm wait", "ex2 g3 + max + sums + exchange", "(rescale) + P tail", "fence + arrive"]
-print("first softmax warp, cycles per phase (blocks 8..15); last column = block period")
+names = ["wait S_j + ldtm + release S buffer", "row max + running-max handover", "128 x ex2 + sums, packs, P stores",
+         "wait PV_{j-1} / rescale O", "P visible + arrive"]
+print("first softmax warp of the even-block set: cycles per phase, own blocks 8, 10, ..; period = two key blocks")
+for j in range(8, 22, 2):
+    t = tr[j]
+    ph = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4]]
+    print(j, dict(zip(names, ph)), "busy", t[5] - t[0], "period(2 blocks)", tr[j + 2][0] - t[0])
+print("S-issuing warp, per key block")
 for j in range(8, 16):
     t = tr[j]
-    ph = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[6] - t[4], t[7] - t[6]]
-    print(j, dict(zip(names, ph)), "period", tr[j + 1][0] - t[0])
-print("MMA warp (two key stages)")
-for j in range(8, 16):
-    t = tr[j]
-    print(j, {"wait_P": t[9] - t[8], "wait_K": t[11] - t[9], "issue_S": t[12] - t[11], "wait_V": t[10] - t[12], "issue_PV": t[13] - t[10],
-              "iter_period": tr[j + 1][8] - t[8]})
+    print(j, {"wait K_j and S buffer free": t[9] - t[8], "issue 8 MMAs + commits": t[10] - t[9], "period": tr[j + 1][8] - t[8]})
