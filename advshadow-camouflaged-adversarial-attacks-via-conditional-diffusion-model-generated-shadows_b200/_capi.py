@@ -35,7 +35,7 @@ class ConvParams(C.Structure):
         ("heads", C.c_int32), ("qk_scale", C.c_float),
         ("dtype", C.c_int32), ("cout_valid", C.c_int32),
         ("stats_partial", C.c_void_p),
-        ("up_phase", C.c_int32), ("reserved", C.c_int32),
+        ("up_phase", C.c_int32), ("stats_gran", C.c_int32),
     ]
 
 
@@ -57,6 +57,7 @@ SIGNATURES = {
     "advs_groupnorm_partial_parts": (C.c_int, [_i, _i]),
     "advs_groupnorm_partial": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "advs_groupnorm_finalize": (C.c_int, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "advs_groupnorm_finalize_ex": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "advs_conv_sm100_stats_parts": (C.c_int, [_i, _i, _i]),
     "advs_groupnorm_apply": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "advs_conv_simt": (C.c_int, [C.POINTER(ConvParams), _vp]),

@@ -175,18 +175,9 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
           epilogue_write32(a.epi, v, m, b, t, n);
         }
         if (want_stats) {
-          // GroupNorm statistics of the tensor just written, per channel (taken before the bf16 rounding:
-          // the rounding error is zero-mean and ~1e-6 of the variance)
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = valid ? v[j] : 0.f;
-            v[j] = x;
-            sq[j] = x * x;
-          }
-          const float cs = warp_column_sums(v, lane);
-          const float cq = warp_column_sums(sq, lane);
-          stat_smem[(acc * 4 + q) * BN + chunk * 32 + lane] = make_float2(cs, cq);
+          // GroupNorm statistics of the tensor just written (taken before the bf16 rounding: the rounding
+          // error is zero-mean and ~1e-6 of the variance)
+          stats_stage(stat_smem, a, BN, acc, q, chunk, lane, warp_stats32(v, valid, lane, a.stats_gran));
         }
       }
       tc_fence_before();
@@ -194,16 +185,7 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (want_stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
-        const int e = (warp - 2) * 32 + lane;
-        for (int c = e; c < BN; c += 256) {
-          const int n = n_tile * BN + c;
-          if (n < a.Cout) {
-            float2 t0 = stat_smem[(acc * 4 + 0) * BN + c], t1 = stat_smem[(acc * 4 + 1) * BN + c];
-            float2 t2 = stat_smem[(acc * 4 + 2) * BN + c], t3 = stat_smem[(acc * 4 + 3) * BN + c];
-            reinterpret_cast<float2*>(a.stats)[(size_t)((m_tile / a.stats_tpi) * a.stats_rpi + a.stats_off + m_tile % a.stats_tpi) * a.Cout + n] =
-                make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
-          }
-        }
+        stats_flush(stat_smem, a, BN, acc, n_tile, m_tile, (warp - 2) * 32 + lane);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -341,7 +323,9 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   a.stats_rpi = a.up ? 4 * a.stats_tpi : a.stats_tpi;
   a.stats_off = a.up ? (p->up_phase - 1) * a.stats_tpi : 0;
   a.stats = p->stats_partial;
+  a.stats_gran = p->stats_gran == 4 ? 4 : 1;
   if (a.stats) {
+    ADVS_CHECK_ARG(p->stats_gran == 0 || p->stats_gran == 1 || p->stats_gran == 4, "conv_sm100_plan: stats_gran must be 0, 1 or 4");
     ADVS_CHECK_ARG(p->out_mode == 0, "conv_sm100_plan: stats_partial needs out_mode 0");
     ADVS_CHECK_ARG(a.tn == 1, "conv_sm100_plan: stats_partial needs tiles that do not span images (H*W >= 128)");
   }

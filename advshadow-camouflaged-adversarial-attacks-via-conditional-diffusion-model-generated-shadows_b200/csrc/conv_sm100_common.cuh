@@ -23,6 +23,7 @@ struct ConvArgs {
   uint32_t a_bytes_seg[3];   // halo kernel: bytes of the activation box of each K-segment
   float* stats;   // optional per-tile channel sums / sums of squares (GroupNorm fusion)
   int stats_tpi, stats_rpi, stats_off;   // row = (m_tile / tpi) * rpi + off + m_tile % tpi
+  int stats_gran;                        // 1: one {sum, sumsq} per channel; 4: per 4 consecutive channels
   int up_a, up_b, up;                    // upsample phase: output pixel (2h+a, 2w+b); up = 0/1
   EpilogueParams epi;
 };
@@ -149,5 +150,71 @@ __device__ __forceinline__ float warp_column_sums(float* v, int lane) {
   return v[0];
 }
 
+// GroupNorm statistics of the 32 rows x 32 columns a warp holds (v[i] of lane l = row l, column i; rows that are
+// not valid count as zero).  gran = 1: lane l returns {sum, sumsq} of column l (31 shuffles per quantity).
+// gran = 4: the four columns of a channel quad are added in the thread first, then 8 values go through the
+// exchange: 9 shuffles per quantity; lanes 0..7 return quad (lane) -- every GroupNorm on the path has a multiple
+// of four channels per group, and the partial rows shrink fourfold.
+__device__ __forceinline__ float2 warp_stats32(float* v, bool valid, int lane, int gran) {
+  if (gran == 4) {
+    float g[8], gq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a0 = valid ? v[4 * k] : 0.f, a1 = valid ? v[4 * k + 1] : 0.f;
+      const float a2 = valid ? v[4 * k + 2] : 0.f, a3 = valid ? v[4 * k + 3] : 0.f;
+      g[k] = (a0 + a1) + (a2 + a3);
+      gq[k] = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, a3 * a3)));
+    }
+#pragma unroll
+    for (int s = 4; s >= 1; s >>= 1) {
+      const bool upper = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float keep = upper ? g[i + s] : g[i], send = upper ? g[i] : g[i + s];
+        g[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        const float keepq = upper ? gq[i + s] : gq[i], sendq = upper ? gq[i] : gq[i + s];
+        gq[i] = keepq + __shfl_xor_sync(0xffffffffu, sendq, s);
+      }
+    }
+    float cs = g[0], cq = gq[0];
+    cs += __shfl_xor_sync(0xffffffffu, cs, 8);
+    cq += __shfl_xor_sync(0xffffffffu, cq, 8);
+    cs += __shfl_xor_sync(0xffffffffu, cs, 16);
+    cq += __shfl_xor_sync(0xffffffffu, cq, 16);
+    return make_float2(cs, cq);
+  }
+  float sq[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = valid ? v[j] : 0.f;
+    v[j] = x;
+    sq[j] = x * x;
+  }
+  const float cs = warp_column_sums(v, lane);
+  const float cq = warp_column_sums(sq, lane);
+  return make_float2(cs, cq);
+}
+
+// stat_smem: [2 accumulators][4 row quarters][bn / gran] float2.  One warp's 32-column chunk:
+__device__ __forceinline__ void stats_stage(float2* stat_smem, const ConvArgs& a, int bn, int acc, int q, int chunk, int lane,
+                                            float2 st) {
+  const int per = 32 / a.stats_gran;
+  if (lane < per) stat_smem[(acc * 4 + q) * (bn / a.stats_gran) + chunk * per + lane] = st;
+}
+// the 256 epilogue threads add the four row quarters of a finished tile and write its partial row
+__device__ __forceinline__ void stats_flush(const float2* stat_smem, const ConvArgs& a, int bn, int acc, int n_tile, int m_tile,
+                                            int e) {
+  const int slots = bn / a.stats_gran, total = a.Cout / a.stats_gran;
+  const size_t prow = (size_t)((m_tile / a.stats_tpi) * a.stats_rpi + a.stats_off + m_tile % a.stats_tpi);
+  for (int c = e; c < slots; c += 256) {
+    const int n = n_tile * slots + c;
+    if (n < total) {
+      const float2 t0 = stat_smem[(acc * 4 + 0) * slots + c], t1 = stat_smem[(acc * 4 + 1) * slots + c];
+      const float2 t2 = stat_smem[(acc * 4 + 2) * slots + c], t3 = stat_smem[(acc * 4 + 3) * slots + c];
+      reinterpret_cast<float2*>(a.stats)[prow * total + n] =
+          make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
+    }
+  }
+}
 
 }  // namespace advs

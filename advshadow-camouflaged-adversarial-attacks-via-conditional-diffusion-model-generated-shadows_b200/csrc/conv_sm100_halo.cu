@@ -213,16 +213,9 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
           epilogue_write32(a.epi, v, m, b, t, n);
         }
         if (want_stats) {
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = valid ? v[j] : 0.f;
-            v[j] = x;
-            sq[j] = x * x;
-          }
-          const float cs = warp_column_sums(v, lane);
-          const float cq = warp_column_sums(sq, lane);
-          stat_smem[(acc * 4 + q) * BN + chunk * 32 + lane] = make_float2(cs, cq);
+          // GroupNorm statistics of the tensor just written (taken before the bf16 rounding: the rounding
+          // error is zero-mean and ~1e-6 of the variance)
+          stats_stage(stat_smem, a, BN, acc, q, chunk, lane, warp_stats32(v, valid, lane, a.stats_gran));
         }
       }
       tc_fence_before();
@@ -230,18 +223,7 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
       if (want_stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int e = (warp - 2) * 32 + lane;
-        if (m_tile < a.m_tiles) {
-          for (int c = e; c < BN; c += 256) {
-            const int n = n_tile * BN + c;
-            if (n < a.Cout) {
-              float2 t0 = stat_smem[(acc * 4 + 0) * BN + c], t1 = stat_smem[(acc * 4 + 1) * BN + c];
-              float2 t2 = stat_smem[(acc * 4 + 2) * BN + c], t3 = stat_smem[(acc * 4 + 3) * BN + c];
-              reinterpret_cast<float2*>(a.stats)[(size_t)((m_tile / a.stats_tpi) * a.stats_rpi + a.stats_off + m_tile % a.stats_tpi) * a.Cout + n] =
-                  make_float2((t0.x + t1.x) + (t2.x + t3.x), (t0.y + t1.y) + (t2.y + t3.y));
-            }
-          }
-        }
+        if (m_tile < a.m_tiles) stats_flush(stat_smem, a, BN, acc, n_tile, m_tile, (warp - 2) * 32 + lane);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

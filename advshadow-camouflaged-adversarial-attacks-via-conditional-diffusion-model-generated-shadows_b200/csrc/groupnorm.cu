@@ -105,8 +105,8 @@ __global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot
 // one 128-thread CTA per (image, group); the group's channels may straddle the two concatenated sources.
 // part_s layout: [B][parts_s][C_s][2].  Threads sweep (part, channel-in-group) pairs with the channel
 // fastest, so each warp reads contiguous float2 runs; fp64 accumulation, fixed reduction order.
-__global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ part0, int c0, int parts0,
-                                                     const float* __restrict__ part1, int c1, int parts1, int groups,
+__global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ part0, int c0, int parts0, int gran0,
+                                                     const float* __restrict__ part1, int c1, int parts1, int gran1, int groups,
                                                      int HW, float eps, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float* __restrict__ scale_shift) {
   __shared__ double red[2][4];
@@ -118,12 +118,14 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ p
 #pragma unroll
   for (int src = 0; src < 2; ++src) {
     const float* base = src == 0 ? part0 : part1;
-    const int C = src == 0 ? c0 : c1, parts = src == 0 ? parts0 : parts1, off = src == 0 ? 0 : c0;
+    const int Cs = src == 0 ? c0 : c1, parts = src == 0 ? parts0 : parts1, off = src == 0 ? 0 : c0;
+    const int gran = src == 0 ? gran0 : gran1;      // channels per partial slot (1 or 4; slots never straddle a group)
     int lo = glo > off ? glo : off;
-    int hi = ghi < off + C ? ghi : off + C;
-    const int n = hi - lo;
-    if (n <= 0 || parts <= 0) continue;
-    const float* p = base + ((size_t)b * parts * C + (lo - off)) * 2;
+    int hi = ghi < off + Cs ? ghi : off + Cs;
+    const int n = (hi - lo) / gran;
+    if (hi <= lo || parts <= 0) continue;
+    const int C = Cs / gran;
+    const float* p = base + ((size_t)b * parts * C + (lo - off) / gran) * 2;
     for (int it = threadIdx.x; it < parts * n; it += 128) {
       const int pi = it / n, cc = it - pi * n;
       const float2 v = *reinterpret_cast<const float2*>(p + ((size_t)pi * C + cc) * 2);
@@ -229,11 +231,11 @@ static int gn_partial_impl(const void* x, int C, int B, int HW, float* part, cud
   return ADVS_OK;
 }
 
-static int gn_finalize_impl(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1, int B,
-                            int HW, int groups, float eps, const float* gamma, const float* beta, float* scale_shift,
-                            cudaStream_t st) {
-  k_gn_finalize<<<B * groups, 128, 0, st>>>(part0, c0, parts0, part1, c1, parts1, groups, HW, eps, gamma, beta,
-                                            scale_shift);
+static int gn_finalize_impl(const float* part0, int c0, int parts0, int gran0, const float* part1, int c1, int parts1,
+                            int gran1, int B, int HW, int groups, float eps, const float* gamma, const float* beta,
+                            float* scale_shift, cudaStream_t st) {
+  k_gn_finalize<<<B * groups, 128, 0, st>>>(part0, c0, parts0, gran0, part1, c1, parts1, gran1, groups, HW, eps, gamma,
+                                            beta, scale_shift);
   ADVS_CHECK_LAUNCH("groupnorm_finalize");
   return ADVS_OK;
 }
@@ -250,7 +252,7 @@ static int gn_stats_impl(const void* x0, int c0, const void* x1, int c1, int B, 
     rc = gn_partial_impl<T>(x1, c1, B, HW, p1, st);
     if (rc) return rc;
   }
-  return gn_finalize_impl(p0, c0, g.chunks, c1 ? p1 : nullptr, c1, c1 ? g.chunks : 0, B, HW, groups, eps, gamma, beta,
+  return gn_finalize_impl(p0, c0, g.chunks, 1, c1 ? p1 : nullptr, c1, c1 ? g.chunks : 0, 1, B, HW, groups, eps, gamma, beta,
                           scale_shift, st);
 }
 
@@ -310,16 +312,27 @@ int advs_groupnorm_partial(const void* x, int C, int B, int HW, float* part, int
   ADVS_CHECK_ARG(false, "groupnorm_partial: bad dtype");
 }
 
-int advs_groupnorm_finalize(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1, int B,
-                            int HW, int groups, float eps, const float* gamma, const float* beta, float* scale_shift,
-                            void* stream) {
+int advs_groupnorm_finalize_ex(const float* part0, int c0, int parts0, int gran0, const float* part1, int c1, int parts1,
+                               int gran1, int B, int HW, int groups, float eps, const float* gamma, const float* beta,
+                               float* scale_shift, void* stream) {
   ADVS_CHECK_ARG(part0 && c0 > 0 && parts0 > 0 && B > 0 && HW > 0 && groups > 0, "groupnorm_finalize: bad args");
-  if (!part1) { c1 = 0; parts1 = 0; }
+  if (!part1) { c1 = 0; parts1 = 0; gran1 = 1; }
   ADVS_CHECK_ARG(c1 == 0 || parts1 > 0, "groupnorm_finalize: second source has no partial rows");
   ADVS_CHECK_ARG((c0 + c1) % groups == 0, "groupnorm_finalize: channels not divisible by groups");
   ADVS_CHECK_ARG(gamma && beta && scale_shift, "groupnorm_finalize: null pointer");
-  return gn_finalize_impl(part0, c0, parts0, part1, c1, parts1, B, HW, groups, eps, gamma, beta, scale_shift,
-                          (cudaStream_t)stream);
+  ADVS_CHECK_ARG((gran0 == 1 || gran0 == 4) && (gran1 == 1 || gran1 == 4), "groupnorm_finalize: gran must be 1 or 4");
+  const int cpg = (c0 + c1) / groups;
+  ADVS_CHECK_ARG((gran0 == 1 && gran1 == 1) || (cpg % 4 == 0 && c0 % 4 == 0 && c1 % 4 == 0),
+                 "groupnorm_finalize: 4-channel partial slots need channels per group and both sources to be multiples of 4");
+  return gn_finalize_impl(part0, c0, parts0, gran0, part1, c1, parts1, gran1, B, HW, groups, eps, gamma, beta,
+                          scale_shift, (cudaStream_t)stream);
+}
+
+int advs_groupnorm_finalize(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1, int B,
+                            int HW, int groups, float eps, const float* gamma, const float* beta, float* scale_shift,
+                            void* stream) {
+  return advs_groupnorm_finalize_ex(part0, c0, parts0, 1, part1, c1, parts1, 1, B, HW, groups, eps, gamma, beta,
+                                    scale_shift, stream);
 }
 
 int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW, const float* scale_shift,

@@ -65,6 +65,17 @@ class UNetEngine:
         # GroupNorm will read
         self._stat_buf = {}
         gn_inputs = {s for op in plan.ops if op.kind == "gn" for s in op.args["srcs"]}
+        # one {sum, sumsq} pair per 4 channels instead of per channel wherever every GroupNorm that reads the
+        # tensor has 4 | channels-per-group and 4 | the tensor's channel offset inside the concat
+        quad_ok = {}
+        for op in plan.ops:
+            if op.kind != "gn":
+                continue
+            ctot, off = sum(plan.shape(s)[3] for s in op.args["srcs"]), 0
+            for sname in op.args["srcs"]:
+                ok = (ctot // op.args["groups"]) % 4 == 0 and off % 4 == 0 and plan.shape(sname)[3] % 4 == 0
+                quad_ok[sname] = quad_ok.get(sname, True) and ok
+                off += plan.shape(sname)[3]
         if fuse_gn_stats:
             for idx, op in enumerate(plan.ops):
                 a = op.args
@@ -76,9 +87,10 @@ class UNetEngine:
                     continue
                 if parts <= 0 or a["dst"] not in gn_inputs:
                     continue
-                name = plan.new_buf("gnpart", (B, parts, a["cout"], 2), "f32")
+                gran = 4 if quad_ok.get(a["dst"], False) else 1
+                name = plan.new_buf("gnpart", (B, parts, a["cout"] // gran, 2), "f32")
                 plan.bufs[name].first, plan.bufs[name].last = idx, plan.bufs[a["dst"]].last
-                self._stat_buf[a["dst"]] = (name, parts)
+                self._stat_buf[a["dst"]] = (name, parts, gran)
         plan.assign_offsets(self.act_bytes)
 
         dev = self.device
@@ -245,17 +257,17 @@ class UNetEngine:
                 for sname in srcs:
                     cs = plan.shape(sname)[3]
                     if sname in self._stat_buf:          # statistics came out of the producing conv's epilogue
-                        pbuf, np_ = self._stat_buf[sname]
-                        parts.append((self._ptr(pbuf), np_))
+                        pbuf, np_, gran = self._stat_buf[sname]
+                        parts.append((self._ptr(pbuf), np_, gran))
                     else:
                         ptr = self._ptr(a["ws"]) + ws_off
                         ws_off += B * chunks * cs * 2 * 4
                         L.append((lib.advs_groupnorm_partial, (self._ptr(sname), cs, B, a["HW"], ptr, dt), "gn_stats"))
-                        parts.append((ptr, chunks))
+                        parts.append((ptr, chunks, 1))
                         self.n_kernels += 1
-                p1, n1 = parts[1] if len(parts) > 1 else (None, 0)
-                L.append((lib.advs_groupnorm_finalize, (parts[0][0], c0, parts[0][1], p1, c1, n1, B, a["HW"], a["groups"],
-                                                        1e-5, g.data_ptr(), bt.data_ptr(), self._ptr(a["ss"])),
+                p1, n1, g1 = parts[1] if len(parts) > 1 else (None, 0, 1)
+                L.append((lib.advs_groupnorm_finalize_ex, (parts[0][0], c0, parts[0][1], parts[0][2], p1, c1, n1, g1, B, a["HW"],
+                                                           a["groups"], 1e-5, g.data_ptr(), bt.data_ptr(), self._ptr(a["ss"])),
                           "gn_finalize"))
                 L.append((lib.advs_groupnorm_apply, (x0, c0, x1, c1, B, a["HW"], self._ptr(a["ss"]),
                                                      1 if a["silu"] else 0, self._ptr(a["dst"]), dt), "gn_apply"))
@@ -284,6 +296,7 @@ class UNetEngine:
                 cp.dtype = dt
                 if a["dst"] in self._stat_buf:
                     cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
+                    cp.stats_gran = self._stat_buf[a["dst"]][2]
                 self._keep.append(cp)
                 if self._conv_sm100_ok(a):
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
@@ -318,6 +331,7 @@ class UNetEngine:
                     cp.bias, cp.out_mode, cp.y, cp.dtype, cp.up_phase = b.data_ptr(), 0, self._ptr(a["dst"]), dt, ph + 1
                     if a["dst"] in self._stat_buf:
                         cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
+                        cp.stats_gran = self._stat_buf[a["dst"]][2]
                     self._keep.append(cp)
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
                     with torch.cuda.device(self.device):

@@ -95,6 +95,11 @@ int advs_groupnorm_partial(const void* x, int C, int B, int HW, float* part, int
 int advs_groupnorm_finalize(const float* part0, int c0, int parts0, const float* part1, int c1, int parts1,
                             int B, int HW, int groups, float eps, const float* gamma, const float* beta,
                             float* scale_shift, void* stream);
+/* same, for partial rows that hold one pair per gran_s consecutive channels (gran_s = 1 or 4; see
+ * advs_conv_params.stats_gran): part_s is [B][parts_s][c_s / gran_s][2]. */
+int advs_groupnorm_finalize_ex(const float* part0, int c0, int parts0, int gran0, const float* part1, int c1, int parts1,
+                               int gran1, int B, int HW, int groups, float eps, const float* gamma, const float* beta,
+                               float* scale_shift, void* stream);
 int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW,
                          const float* scale_shift, int silu, void* y, int dtype, void* stream);
 
@@ -145,7 +150,11 @@ typedef struct advs_conv_params {
    * With up_phase != 0: B,H,W are the INPUT size, y is [B,2H,2W,Cout], segment 0 has taps = 4 and
    * weights from advs_pack_upconv_weight; stats_partial rows are [B][4 * parts][Cout][2]. */
   int32_t up_phase;
-  int32_t reserved;
+  /* granularity of stats_partial: 0 or 1 = one {sum, sumsq} pair per output channel (layout above);
+   * 4 = one pair per 4 consecutive channels, layout [B][parts][Cout/4][2] -- a quarter of the partial traffic and
+   * a third of the epilogue's shuffles; usable whenever every GroupNorm reading the tensor has a multiple of 4
+   * channels per group (pass the same value as gran to advs_groupnorm_finalize_ex). */
+  int32_t stats_gran;
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */

@@ -156,6 +156,40 @@ def test_attention_lazy_rescale_path(ops):
     assert rel_err(o, ref) < 2e-2
 
 
+@pytest.mark.parametrize("T,dh", [(384, 64), (384, 128), (640, 128), (384, 256), (640, 256)])
+def test_attention_odd_block_counts(ops, T, dh):
+    """3 and 5 key blocks: the even-block softmax set runs one block more than the odd-block set."""
+    torch.manual_seed(14)
+    B, heads = 1, 3
+    q = (torch.randn(B, heads, T, dh, device="cuda") * 0.8).to(torch.bfloat16)
+    k = (torch.randn(B, heads, T, dh, device="cuda") * 0.8).to(torch.bfloat16)
+    vt = torch.randn(B, heads, dh, T, device="cuda").to(torch.bfloat16)
+    o = ops.attention(q, k, vt, impl="sm100")
+    p = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()).softmax(-1)
+    ref = torch.einsum("bhts,bhds->bthd", p, vt.float()).reshape(B, T, heads * dh)
+    assert rel_err(o, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("T,dh,top,descending", [(640, 128, 8.0, False), (1024, 64, 8.0, False), (640, 256, 6.0, False),
+                                                 (640, 128, 8.0, True)])
+def test_attention_running_max_handover(ops, T, dh, top, descending):
+    """Row maxima that grow by more than the lazy threshold in EVERY key block (both softmax sets rescale O and
+    correct each other's row sums), and the mirror case where block 0 holds the maximum and nothing ever grows."""
+    torch.manual_seed(15)
+    B, heads = 1, 2
+    q = torch.ones(B, heads, T, dh, device="cuda").to(torch.bfloat16) * 0.25
+    ramp = torch.linspace(0, top, T, device="cuda")
+    if descending:
+        ramp = ramp.flip(0)
+    k = (torch.ones(B, heads, T, dh, device="cuda") * ramp[None, None, :, None] * (32.0 / dh)).to(torch.bfloat16)
+    vt = torch.randn(B, heads, dh, T, device="cuda").to(torch.bfloat16)
+    o = ops.attention(q, k, vt, impl="sm100")
+    p = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()).softmax(-1)
+    ref = torch.einsum("bhts,bhds->bthd", p, vt.float()).reshape(B, T, heads * dh)
+    assert torch.isfinite(o.float()).all()
+    assert rel_err(o, ref) < 2e-2
+
+
 def test_upsample_and_edges(ops):
     torch.manual_seed(6)
     x = torch.randn(2, 5, 7, 64, device="cuda").to(torch.bfloat16)
@@ -243,7 +277,8 @@ def test_head_conv_nchw_f32_output(ops, impl, dtype, tol):
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 128, 256), (3, 8, 32, 64, 192), (1, 4, 256, 128, 128)])
-def test_conv_epilogue_groupnorm_statistics(ops, case):
+@pytest.mark.parametrize("gran", [1, 4])
+def test_conv_epilogue_groupnorm_statistics(ops, case, gran):
     """The tcgen05 conv epilogue can emit per-tile channel sums of the tensor it stores; finalised, they
     must equal the stand-alone GroupNorm statistics kernel run on that tensor (K5 fused into K1)."""
     import ctypes as C
@@ -257,9 +292,10 @@ def test_conv_epilogue_groupnorm_statistics(ops, case):
     wp = ops.pack_conv_weight(w, torch.bfloat16)
     parts = lib.advs_conv_sm100_stats_parts(B, H, W)
     assert parts > 0
-    part = torch.full((B, parts, cout, 2), float("nan"), device="cuda")
+    part = torch.full((B, parts, cout // gran, 2), float("nan"), device="cuda")
     y = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device="cuda")
     cp = capi.ConvParams()
+    cp.stats_gran = gran
     cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, cout, 1, 1
     cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), wp.data_ptr(), cin, 9
     cp.bias, cp.out_mode, cp.y, cp.dtype, cp.stats_partial = bias.data_ptr(), 0, y.data_ptr(), capi.BF16, part.data_ptr()
@@ -270,8 +306,8 @@ def test_conv_epilogue_groupnorm_statistics(ops, case):
     # per-channel sums straight from the stored tensor (the epilogue sums the fp32 values before the bf16
     # rounding: zero-mean differences of relative size 2^-9 per element)
     yf = y.float()
-    ref_sum = yf.sum(dim=(1, 2))
-    ref_sq = (yf * yf).sum(dim=(1, 2))
+    ref_sum = yf.sum(dim=(1, 2)).reshape(B, cout // gran, gran).sum(-1)      # gran 4: one pair per channel quad
+    ref_sq = (yf * yf).sum(dim=(1, 2)).reshape(B, cout // gran, gran).sum(-1)
     got = part.sum(dim=1)
     assert torch.isfinite(part).all()
     assert (got[..., 0] - ref_sum).abs().max() <= 4e-3 * ref_sq.sqrt().max()
@@ -279,8 +315,14 @@ def test_conv_epilogue_groupnorm_statistics(ops, case):
     # finalised scale/shift == the stand-alone statistics path
     g, bt = torch.randn(cout, device="cuda"), torch.randn(cout, device="cuda")
     ss_f = torch.empty(B, cout, 2, device="cuda")
-    capi.call("advs_groupnorm_finalize", part.data_ptr(), cout, parts, None, 0, 0, B, H * W, 32, 1e-5, g.data_ptr(),
-              bt.data_ptr(), ss_f.data_ptr(), st)
+    if gran == 4 and (cout // 32) % 4:
+        # quads would straddle group boundaries: the finaliser refuses instead of mixing groups
+        with pytest.raises(capi.AdvsError):
+            capi.call("advs_groupnorm_finalize_ex", part.data_ptr(), cout, parts, gran, None, 0, 0, 1, B, H * W, 32, 1e-5,
+                      g.data_ptr(), bt.data_ptr(), ss_f.data_ptr(), st)
+        return
+    capi.call("advs_groupnorm_finalize_ex", part.data_ptr(), cout, parts, gran, None, 0, 0, 1, B, H * W, 32, 1e-5,
+              g.data_ptr(), bt.data_ptr(), ss_f.data_ptr(), st)
     ss_s = torch.empty(B, cout, 2, device="cuda")
     wsb = lib.advs_groupnorm_workspace_bytes(B, H * W, cout)
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
@@ -290,7 +332,8 @@ def test_conv_epilogue_groupnorm_statistics(ops, case):
 
 
 @pytest.mark.parametrize("case", [(2, 8, 16, 128, 128), (1, 32, 32, 64, 192), (1, 2, 128, 64, 64)])
-def test_upsample_conv_as_four_phase_convs(ops, case):
+@pytest.mark.parametrize("gran", [1, 4])
+def test_upsample_conv_as_four_phase_convs(ops, case, gran):
     """Upsample (dm1:129-140): nearest 2x + conv3x3 == four 2x2 convolutions on the low-res tensor with
     pre-summed weights (advs_pack_upconv_weight), each writing one parity class of the output pixels;
     the fused GroupNorm partial statistics cover the whole high-res tensor."""
@@ -307,7 +350,7 @@ def test_upsample_conv_as_four_phase_convs(ops, case):
     capi.call("advs_pack_upconv_weight", w.data_ptr(), w4.data_ptr(), cout, cin, capi.BF16, st)
     y = torch.full((B, 2 * H, 2 * W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     parts = lib.advs_conv_sm100_stats_parts(B, H, W)
-    part = torch.full((B, 4 * parts, cout, 2), float("nan"), device="cuda") if parts else None
+    part = torch.full((B, 4 * parts, cout // gran, 2), float("nan"), device="cuda") if parts else None
     keep = []
     for ph in range(4):
         cp = capi.ConvParams()
@@ -315,7 +358,7 @@ def test_upsample_conv_as_four_phase_convs(ops, case):
         cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), w4[ph].data_ptr(), cin, 4
         cp.bias, cp.out_mode, cp.y, cp.dtype, cp.up_phase = bias.data_ptr(), 0, y.data_ptr(), capi.BF16, ph + 1
         if part is not None:
-            cp.stats_partial = part.data_ptr()
+            cp.stats_partial, cp.stats_gran = part.data_ptr(), gran
         pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
         capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
         capi.call("advs_conv_sm100_launch", pb.ptr, st)
@@ -325,4 +368,5 @@ def test_upsample_conv_as_four_phase_convs(ops, case):
     if part is not None:
         yf = y.float()
         assert torch.isfinite(part).all()
-        assert ((part.sum(1)[..., 1] - (yf * yf).sum(dim=(1, 2))).abs() / (yf * yf).sum(dim=(1, 2))).max() < 2e-3
+        ref_sq = (yf * yf).sum(dim=(1, 2)).reshape(B, cout // gran, gran).sum(-1)
+        assert ((part.sum(1)[..., 1] - ref_sq).abs() / ref_sq).max() < 2e-3

@@ -56,7 +56,7 @@ def loop(fn, seconds=3.0):
     return e0.elapsed_time(e1) / n / 1e3, t0, t1
 
 
-def conv_case(B, H, W, cin, cout, taps, stats=False):
+def conv_case(B, H, W, cin, cout, taps, stats=0):
     x = torch.randn(B, H, W, cin, device="cuda").to(torch.bfloat16)
     k = 3 if taps == 9 else 1
     w = ops.pack_conv_weight(torch.randn(cout, cin, k, k, device="cuda") / 30, torch.bfloat16)
@@ -69,8 +69,8 @@ def conv_case(B, H, W, cin, cout, taps, stats=False):
     keep = [x, w, y, bias]
     if stats:
         parts = capi.lib().advs_conv_sm100_stats_parts(B, H, W)
-        part = torch.empty(B, parts, cout, 2, device="cuda")
-        cp.stats_partial = part.data_ptr()
+        part = torch.empty(B, parts, cout // stats, 2, device="cuda")
+        cp.stats_partial, cp.stats_gran = part.data_ptr(), stats
         keep.append(part)
     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
     capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
@@ -93,11 +93,11 @@ def main():
              ("512->512 3x3 @64^2 B64", (64, 64, 64, 512, 512, 9)), ("1024->1024 3x3 @32^2 B64", (64, 32, 32, 1024, 1024, 9)),
              ("512->512 1x1 @64^2 B64", (64, 64, 64, 512, 512, 1))]
     for name, c in cases:
-        for stats in (False, True):
+        for stats in (0, 1, 4):
             fn, flops, keep = conv_case(*c, stats=stats)
             per, t0, t1 = loop(fn)
             clk, pw = smi.window(t0, t1)
-            out.append(dict(case=name + (" +gn-stats" if stats else ""), tflops=flops / per / 1e12, ms=per * 1e3, sm_mhz=clk, watts=pw))
+            out.append(dict(case=name + ({0: "", 1: " +gn-stats per channel", 4: " +gn-stats per 4 channels"}[stats]), tflops=flops / per / 1e12, ms=per * 1e3, sm_mhz=clk, watts=pw))
             print(out[-1], flush=True)
             del keep
     for (T, dh) in ((4096, 128), (1024, 256)):
