@@ -58,6 +58,8 @@ SIGNATURES = {
     "advs_groupnorm_partial": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "advs_groupnorm_finalize": (C.c_int, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "advs_groupnorm_finalize_ex": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "advs_stem_im2col": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "advs_pack_stem_weight": (C.c_int, [_vp, _vp, _i, _i, _vp]),
     "advs_conv_sm100_stats_parts": (C.c_int, [_i, _i, _i]),
     "advs_groupnorm_apply": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "advs_conv_simt": (C.c_int, [C.POINTER(ConvParams), _vp]),

@@ -53,6 +53,56 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ 
 }
 
 // OIHW 3x3 fp32 -> [phase][O][4][I] T (nearest-2x upsample folded into the kernel, see header)
+// Stem (Cin = 3) on the tensor cores: the 3x3 neighbourhood of the fp32 NCHW input becomes one 64-entry bf16 row
+// per pixel, so the stem is a 1x1 convolution with 64 input "channels" for the implicit-GEMM kernel.
+// entry = part * 9*Cin + tap * Cin + ci; part 0 = bf16(x), part 1 = bf16(x - bf16(x)) when it fits (the fp32
+// sampler state then reaches the bf16 MMA to ~2^-17 instead of 2^-9), the rest is zero.  Zero padding of the
+// convolution = zeros here.  One thread per (pixel, 8 entries): 16-byte stores, 128 contiguous bytes per pixel.
+// CIN > 0: compile-time channel count (the divisions below fold into constants); CIN = 0: run-time Cin.
+template <int CIN>
+__global__ void k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int H, int W, int cin_rt,
+                              int parts) {
+  const int Cin = CIN > 0 ? CIN : cin_rt;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t npix = (size_t)B * H * W;
+  if (idx >= npix * 8) return;
+  const size_t pix = idx >> 3;
+  const int chunk = (int)(idx & 7);
+  const int w0 = (int)(pix % W), h0 = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+  const int k9 = 9 * Cin;
+  uint32_t packed[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    float v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int slot = chunk * 8 + e + u;
+      const int part = slot / k9, r = slot - part * k9;
+      const int tap = r / Cin, ci = r - tap * Cin;
+      const int hh = h0 + tap / 3 - 1, ww = w0 + tap % 3 - 1;
+      float val = 0.f;
+      if (part < parts && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        val = __ldg(x + (((size_t)b * Cin + ci) * H + hh) * W + ww);
+        if (part == 1) val -= __bfloat162float(__float2bfloat16_rn(val));
+      }
+      v[u] = val;
+    }
+    packed[e >> 1] = pack_bf16x2(v[0], v[1]);
+  }
+  *reinterpret_cast<uint4*>(col + pix * 64 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// matching weight rows [O][64]: both parts carry bf16(w[o][ci][tap])
+__global__ void k_pack_stem_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int O, int I, int parts) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)O * 64) return;
+  const int o = (int)(idx >> 6), slot = (int)(idx & 63);
+  const int k9 = 9 * I;
+  const int part = slot / k9, r = slot - part * k9;
+  const int tap = r / I, ci = r - tap * I;
+  dst[idx] = __float2bfloat16_rn(part < parts ? w[((size_t)o * I + ci) * 9 + tap] : 0.f);
+}
+
 template <typename T>
 __global__ void k_pack_upconv_weight(const float* __restrict__ w, T* __restrict__ dst, int O, int I) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,6 +377,27 @@ int advs_pack_upconv_weight(const float* w, void* dst, int O, int I, int dtype, 
   else
     ADVS_CHECK_ARG(false, "pack_upconv_weight: bad dtype");
   ADVS_CHECK_LAUNCH("pack_upconv_weight");
+  return ADVS_OK;
+}
+
+int advs_stem_im2col(const float* x, void* col, int B, int H, int W, int Cin, void* stream) {
+  ADVS_CHECK_ARG(x && col && B > 0 && H > 0 && W > 0 && Cin > 0 && 9 * Cin <= 64, "stem_im2col: bad args (needs 9*Cin <= 64)");
+  const size_t n = (size_t)B * H * W * 8;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (Cin == 3)
+    k_stem_im2col<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin, 2);
+  else
+    k_stem_im2col<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin, 18 * Cin <= 64 ? 2 : 1);
+  ADVS_CHECK_LAUNCH("stem_im2col");
+  return ADVS_OK;
+}
+
+int advs_pack_stem_weight(const float* w, void* dst, int O, int I, void* stream) {
+  ADVS_CHECK_ARG(w && dst && O > 0 && I > 0 && 9 * I <= 64, "pack_stem_weight: bad args (needs 9*I <= 64)");
+  const size_t n = (size_t)O * 64;
+  k_pack_stem_weight<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, O, I,
+                                                                                    18 * I <= 64 ? 2 : 1);
+  ADVS_CHECK_LAUNCH("pack_stem_weight");
   return ADVS_OK;
 }
 

@@ -83,6 +83,8 @@ class UNetEngine:
                     parts = 4 * int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
                 elif op.kind == "conv" and a["qkv"] is None and self._conv_sm100_ok(a):
                     parts = int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
+                elif op.kind == "stem" and self._stem_sm100_ok(a):
+                    parts = int(self.lib.advs_conv_sm100_stats_parts(B, a["H"], a["W"]))
                 else:
                     continue
                 if parts <= 0 or a["dst"] not in gn_inputs:
@@ -126,6 +128,10 @@ class UNetEngine:
             return False
         return True
 
+    def _stem_sm100_ok(self, a):
+        # Cin = 3 stem as a 64-wide 1x1 conv on the tensor cores (im2col rows, csrc/elementwise.cu)
+        return self.conv_impl == "sm100" and 9 * a["cin"] <= 64 and a["cout"] % 64 == 0
+
     def _head_sm100_ok(self, a):
         return self.conv_impl == "sm100" and a["cin"] % 64 == 0 and a["cout"] <= 64
 
@@ -146,7 +152,11 @@ class UNetEngine:
         for op in self.plan.ops:
             a = op.args
             if op.kind == "stem":
-                self._packed[(a["weight"], None)] = torch.empty(a["cout"], 9, a["cin"], dtype=torch.float32, device=dev)
+                if self._stem_sm100_ok(a):
+                    self._packed[(a["weight"], "stem64")] = torch.empty(a["cout"], 1, 64, dtype=tdt, device=dev)
+                    self._stem_col = torch.empty(self.B, a["H"], a["W"], 64, dtype=tdt, device=dev)
+                else:
+                    self._packed[(a["weight"], None)] = torch.empty(a["cout"], 9, a["cin"], dtype=torch.float32, device=dev)
                 self._bias[(a["weight"],)] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
             elif op.kind == "head":
                 # the head runs through the implicit-GEMM conv (fp32 NCHW epilogue); on the tcgen05 path
@@ -188,6 +198,9 @@ class UNetEngine:
                     capi.call("advs_pack_upconv_weight", w.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1],
                               capi.BF16 if dst.dtype == torch.bfloat16 else capi.F32, st)
                     continue
+                if sl == "stem64":
+                    capi.call("advs_pack_stem_weight", w.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1], st)
+                    continue
                 if sl is not None:
                     w = w[:, sl[0]:sl[1]].contiguous()
                 O, I, kh, kw = w.shape          # dst may have more (zero) rows than O: the padded head
@@ -225,7 +238,25 @@ class UNetEngine:
         self.n_kernels = 0
         for op in plan.ops:
             a = op.args
-            if op.kind == "stem":
+            if op.kind == "stem" and self._stem_sm100_ok(a):
+                w, b = self._packed[(a["weight"], "stem64")], self._bias[(a["weight"],)]
+                L.append((lib.advs_stem_im2col, (self.x.data_ptr(), self._stem_col.data_ptr(), B, a["H"], a["W"], a["cin"]),
+                          "stem_im2col"))
+                cp = capi.ConvParams()
+                cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], a["cout"], 1, 1
+                cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = self._stem_col.data_ptr(), w.data_ptr(), 64, 1
+                cp.bias, cp.out_mode, cp.y, cp.dtype = b.data_ptr(), 0, self._ptr(a["dst"]), dt
+                if a["dst"] in self._stat_buf:
+                    cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
+                    cp.stats_gran = self._stat_buf[a["dst"]][2]
+                self._keep.append(cp)
+                pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+                with torch.cuda.device(self.device):
+                    capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+                self._plans.append(pb)
+                L.append((lib.advs_conv_sm100_launch, (pb.ptr,), "stem_sm100"))
+                self.n_kernels += 2
+            elif op.kind == "stem":
                 w, b = self._packed[(a["weight"], None)], self._bias[(a["weight"],)]
                 L.append((lib.advs_conv3x3_stem, (self.x.data_ptr(), w.data_ptr(), b.data_ptr(), self._ptr(a["dst"]),
                                                   B, a["H"], a["W"], a["cin"], a["cout"], dt), "stem"))
@@ -431,6 +462,10 @@ class UNetEngine:
             elif op.kind == "up":
                 n = self.B * a["H"] * a["W"] * a["C"]
                 out.append(("upsample", 0, 5 * n * ab))
+            elif op.kind == "stem" and self._stem_sm100_ok(a):
+                m = self.B * a["H"] * a["W"]
+                out.append(("stem_im2col", 0, m * (a["cin"] * 4 + 64 * ab)))
+                out.append(("stem_sm100", 2 * m * 9 * a["cin"] * a["cout"], m * (64 + a["cout"]) * ab))
             elif op.kind == "stem":
                 m = self.B * a["H"] * a["W"]
                 out.append(("stem", 2 * m * 9 * a["cin"] * a["cout"], m * (a["cin"] * 4 + a["cout"] * ab)))

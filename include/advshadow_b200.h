@@ -72,6 +72,12 @@ int advs_pack_upconv_weight(const float* w_oihw, void* dst, int O, int I, int dt
 /* x NCHW fp32 [B,Cin,H,W], w fp32 [Cout][9][Cin], y NHWC `dtype` [B,H,W,Cout]. 3x3, pad 1. */
 int advs_conv3x3_stem(const float* x_nchw, const float* w, const float* bias, void* y, int B,
                       int H, int W, int Cin, int Cout, int dtype, void* stream);
+/* The same stem on the tensor cores (9*Cin <= 64): advs_stem_im2col turns the fp32 NCHW input into bf16 rows
+ * col[B,H,W,64] (entry = part*9*Cin + tap*Cin + ci; part 0 = bf16(x), part 1 = bf16(x - bf16(x)) when 18*Cin <= 64,
+ * rest 0), advs_pack_stem_weight writes the matching bf16 rows [Cout][64]; the stem is then a 1x1 convolution
+ * (advs_conv_sm100_plan with one segment, C = 64, taps = 1) with the usual fused epilogue. */
+int advs_stem_im2col(const float* x_nchw, void* col, int B, int H, int W, int Cin, void* stream);
+int advs_pack_stem_weight(const float* w_oihw, void* dst, int O, int I, void* stream);
 /* x NHWC `dtype` [B,H,W,Cin], w fp32 [Cout][9][Cin], y NCHW fp32 [B,Cout,H,W]. 3x3, pad 1. */
 int advs_conv3x3_head(const void* x, const float* w, const float* bias, float* y_nchw, int B,
                       int H, int W, int Cin, int Cout, int dtype, void* stream);

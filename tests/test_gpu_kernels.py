@@ -276,6 +276,41 @@ def test_head_conv_nchw_f32_output(ops, impl, dtype, tol):
     assert rel_err(y2, ref) < tol
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 3, 128), (1, 9, 130, 3, 64), (1, 32, 32, 6, 128)])
+def test_stem_on_tensor_cores(ops, case):
+    """Cin = 3 stem (dm1:192) as im2col rows + a 64-wide 1x1 tcgen05 conv.  With the hi/lo split of the fp32 input
+    (18*Cin <= 64) the only rounding left is the bf16 weights and the bf16 output."""
+    import ctypes as C
+    from advshadow_b200 import _capi as capi
+    B, H, W, cin, cout = case
+    torch.manual_seed(12)
+    x = torch.randn(B, cin, H, W, device="cuda") * 1.5
+    w = torch.randn(cout, cin, 3, 3, device="cuda") / 5
+    bias = torch.randn(cout, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    col = torch.full((B, H, W, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    w64 = torch.full((cout, 1, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    capi.call("advs_stem_im2col", x.data_ptr(), col.data_ptr(), B, H, W, cin, st)
+    capi.call("advs_pack_stem_weight", w.data_ptr(), w64.data_ptr(), cout, cin, st)
+    assert torch.isfinite(col.float()).all() and torch.isfinite(w64.float()).all()
+    y = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device="cuda")
+    cp = capi.ConvParams()
+    cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, cout, 1, 1
+    cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = col.data_ptr(), w64.data_ptr(), 64, 1
+    cp.bias, cp.out_mode, cp.y, cp.dtype = bias.data_ptr(), 0, y.data_ptr(), capi.BF16
+    pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+    capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+    capi.call("advs_conv_sm100_launch", pb.ptr, st)
+    wq = w.to(torch.bfloat16).float()
+    ref = F.conv2d(x, wq, bias, padding=1)
+    # vs the same bf16 weights: input exact to ~2^-17 when the lo part fits, else bf16 inputs as well
+    assert rel_err(nchw(y), ref) < (3e-3 if 18 * cin <= 64 else 6e-3)
+    if 18 * cin <= 64:
+        # before the output rounding the GEMM reproduces the fp32-input convolution: check through the row sums
+        got = torch.einsum("bhwk,ok->bhwo", col.float(), w64[:, 0].float()) + bias
+        assert (got - ref.permute(0, 2, 3, 1)).abs().max() < 2e-4 * ref.abs().max()
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 128, 256), (3, 8, 32, 64, 192), (1, 4, 256, 128, 128)])
 @pytest.mark.parametrize("gran", [1, 4])
 def test_conv_epilogue_groupnorm_statistics(ops, case, gran):
