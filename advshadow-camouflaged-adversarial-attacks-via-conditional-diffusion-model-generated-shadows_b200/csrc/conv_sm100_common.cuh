@@ -54,6 +54,20 @@ struct ConvCfg {
   static constexpr uint32_t tmem_cols = 2 * BN;
 };
 
+// 256-bit global accesses (sm_100): a thread's 32 output channels are two 32-byte pieces instead of four
+// 16-byte ones.  Every thread of the warp is on a different pixel row, so each access instruction touches 32
+// cache lines whatever its width -- halving the instruction count halves the LSU time of the epilogue.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+
 // 32 consecutive output channels [n, n+32) of one pixel row: v = acc + bias + temb + residual
 __device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, const uint32_t* acc, float* v, size_t m,
                                                    int b, int n) {
@@ -76,16 +90,17 @@ __device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, cons
     }
   }
   if (e.out_mode == 0 && e.residual) {
-    const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.Cout + n);
+    const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + m * e.Cout + n;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 r4 = __ldg(rp + j);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+    for (int j = 0; j < 2; ++j) {
+      uint32_t r8[8];
+      ld_global_nc_256(rp + 16 * j, r8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(r8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 8; ++i) {
         float2 f = __bfloat1622float2(h[i]);
-        v[8 * j + 2 * i] += f.x;
-        v[8 * j + 2 * i + 1] += f.y;
+        v[16 * j + 2 * i] += f.x;
+        v[16 * j + 2 * i + 1] += f.y;
       }
     }
   }
@@ -93,15 +108,13 @@ __device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, cons
 
 __device__ __forceinline__ void epilogue_write32(const EpilogueParams& e, const float* v, size_t m, int b, int t, int n) {
   if (e.out_mode == 0) {
-    uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n);
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 o;
-      o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]);
-      o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-      o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-      o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-      yp[j] = o;
+    for (int j = 0; j < 2; ++j) {
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
+      st_global_256(yp + 16 * j, o);
     }
   } else if (e.out_mode == 2) {
     float* dst = reinterpret_cast<float*>(e.y) + ((size_t)b * e.cout_valid + n) * e.HW + t;

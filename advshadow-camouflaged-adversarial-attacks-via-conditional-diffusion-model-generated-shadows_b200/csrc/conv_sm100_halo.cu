@@ -15,6 +15,13 @@
 
 namespace advs {
 
+#ifdef ADVS_ATTN_TRACE   // debug build (make trace): clock64 stamps of CTA 0's first epilogue warp and of the MMA warp
+__device__ long long g_conv_trace[64 * 16];
+#define CTR(slot) do { if (blockIdx.x == 0 && lane == 0 && tix < 64) g_conv_trace[tix * 16 + (slot)] = clock64(); } while (0)
+#else
+#define CTR(slot) do { } while (0)
+#endif
+
 template <int BN>
 struct ConvCfgH {
   static constexpr uint32_t b_bytes = (BN / 2) * 128;          // this CTA's half of one tap's weight tile
@@ -24,12 +31,17 @@ struct ConvCfgH {
   // issuing warp, so three taps (one kernel row) share a ring stage and a barrier round trip
   static constexpr int tps = (BN == 256) ? 1 : 3;              // taps per weight-ring stage
   static constexpr uint32_t stage_bytes = tps * b_bytes;
-  static constexpr int stages = (BN == 256) ? 6 : 4;           // weight-tile ring
+  static constexpr int stages = (BN == 256) ? 6 : 4;           // weight-tile ring (BN = 128: 3 / 4 / 5 stages measured
+                                                               // 6 200 / 5 400 / 5 400 cycles per tile)
   static constexpr uint32_t off_b = a_bufs * a_buf_bytes;
   static constexpr uint32_t off_bar = off_b + stages * stage_bytes;
-  static constexpr uint32_t bar_bytes = 512;
+  static constexpr uint32_t bar_bytes = 256;                   // 2 * stages + 2 * a_bufs + 4 mbarriers + the TMEM slot
   static constexpr uint32_t stat_bytes = 2 * 4 * BN * 8;
-  static constexpr uint32_t smem_bytes = off_bar + bar_bytes + stat_bytes + 1024;
+  // + slack for aligning the dynamic shared-memory base up to 1 KB (the kernel traps if that is ever not enough)
+  static constexpr uint32_t used_bytes = off_bar + bar_bytes + stat_bytes;
+  static constexpr uint32_t smem_bytes = used_bytes + 1024;
+  static_assert(smem_bytes <= 232448, "halo kernel: shared memory over the 227 KB limit");
+  static_assert((2 * stages + 2 * a_bufs + 4) * 8 + 8 <= bar_bytes, "halo kernel: barrier area too small");
   static constexpr uint32_t tmem_cols = 2 * BN;
 };
 
@@ -40,6 +52,7 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
   constexpr int STAGES = Cfg::stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  if ((uint32_t)(smem - smem_raw) + Cfg::used_bytes > Cfg::smem_bytes) __trap();   // base less aligned than assumed
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::off_bar);   // weight ring
   uint64_t* empty = full + STAGES;
   uint64_t* a_full = empty + STAGES;                                   // activation (halo) buffers
@@ -128,9 +141,12 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
       uint32_t phase = 0, aphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = pair; item < total_items; item += num_pairs) {
+      int tix = 0;
+      for (int item = pair; item < total_items; item += num_pairs, ++tix) {
+        CTR(12);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
+        CTR(13);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         uint32_t first = 1;
         for (int s = 0; s < a.nseg; ++s) {
@@ -172,6 +188,7 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
         }
         if (elect_one()) umma_commit_2cta(&tfull[acc], 3);
         __syncwarp();
+        CTR(14);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -183,7 +200,8 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
     const int rows_valid = a.tw * a.th * a.tn;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = pair; item < total_items; item += num_pairs) {
+    int tix = warp == 2 ? 0 : 64;
+    for (int item = pair; item < total_items; item += num_pairs, ++tix) {
       const int m_pair = item / a.n_tiles, n_tile = item - m_pair * a.n_tiles;
       const int m_tile = m_pair * 2 + (int)rank;
       const int w0 = (m_tile % a.tiles_w) * a.tw;
@@ -196,8 +214,10 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
       const bool valid = row < rows_valid && b < a.B && m_tile < a.m_tiles;
       const int t = a.up ? (2 * (h0 + dh) + a.up_a) * (2 * a.W) + 2 * (w0 + dw) + a.up_b : (h0 + dh) * a.W + (w0 + dw);
       const size_t m = (size_t)b * a.epi.HW + t;
+      CTR(0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      CTR(1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool want_stats = a.stats != nullptr;
 #pragma unroll 1
@@ -205,26 +225,34 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + chunk * 32, r);
         tmem_wait_ld();
+        if (chunk == 0) CTR(2);
         const int n = n_tile * BN + chunk * 32;
         if (n >= a.epi.cout_valid) break;
         float v[32];
         if (valid) {
           epilogue_compute32(a.epi, r, v, m, b, n);
+          if (chunk == 0) CTR(3);
           epilogue_write32(a.epi, v, m, b, t, n);
+          if (chunk == 0) CTR(4);
         }
         if (want_stats) {
           // GroupNorm statistics of the tensor just written (taken before the bf16 rounding: the rounding
           // error is zero-mean and ~1e-6 of the variance)
           stats_stage(stat_smem, a, BN, acc, q, chunk, lane, warp_stats32(v, valid, lane, a.stats_gran));
         }
+        if (chunk == 0) CTR(5);
       }
+      CTR(6);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+      CTR(7);
       if (want_stats) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        CTR(8);
         if (m_tile < a.m_tiles) stats_flush(stat_smem, a, BN, acc, n_tile, m_tile, (warp - 2) * 32 + lane);
       }
+      CTR(9);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -234,6 +262,14 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
   cluster_sync_all();          // the peer may still be reading this CTA's smem / signalling its barriers
   if (warp == 1) tmem_dealloc_2cta<Cfg::tmem_cols>(tmem_base);
 }
+
+#ifdef ADVS_ATTN_TRACE
+}  // namespace advs
+extern "C" int advs_debug_conv_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, advs::g_conv_trace, sizeof(long long) * 64 * 16) == cudaSuccess ? 0 : -2;
+}
+namespace advs {
+#endif
 
 uint32_t conv_2cta_halo_smem_bytes(int bn) { return bn == 256 ? ConvCfgH<256>::smem_bytes : ConvCfgH<128>::smem_bytes; }
 
