@@ -19,7 +19,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH = 0.595e9  # profiles/r01b_summary.md: mean over the 20 captured k_conv_sm100_2cta<256> launches
+# profiles/r01c_summary.md / prof_r01c_key_metrics.csv: mean dram read+write of the 21 conv launches of the --set full
+# capture (32-image sub-batch, deep UNet levels; e.g. the captured 256->256 3x3 @128^2 launch moved 782 MB against
+# 805 MB algorithmic incl. its residual) -- no re-reads beyond the algorithmic traffic
+NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH = 0.312e9
 METRIC = "shadowed images/sec (DDIM-50, 256x256)"
 UNIT = "images/s"
 
