@@ -256,8 +256,8 @@ def main():
             "gpu_launches": sampler.launches_per_trajectory * args.steps + args.steps,
             "roofline": {"kernel": "k_conv_sm100_2cta[_halo] (tcgen05 cta_group::2 implicit-GEMM conv, all launches of one UNet forward)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                         # mean dram__bytes_read+write per captured conv launch, profiles/prof_r01b_key_metrics.csv
-                         # (the capture covers 20 deep-level launches; "algorithmic_bytes_per_launch" averages all 105)
+                         # mean dram__bytes_read+write per captured conv launch, profiles/prof_r01c_key_metrics.csv
+                         # (the capture covers 21 deep-level launches; "algorithmic_bytes_per_launch" averages all 105)
                          "traffic": NCU_CONV_TRAFFIC_BYTES_PER_LAUNCH,
                          "algorithmic_bytes_per_launch": conv["bytes"] / max(conv["launches"], 1),
                          "peak_source": peak_src},
