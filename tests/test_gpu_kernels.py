@@ -190,6 +190,62 @@ def test_attention_running_max_handover(ops, T, dh, top, descending):
     assert rel_err(o, ref) < 2e-2
 
 
+def test_attention_repeatable_over_shapes(ops):
+    """Race detector for the warp-specialised attention kernel: random shapes, every launch repeated on the same
+    inputs must be bit-identical (the kernel has no atomics; the only cross-warp traffic goes through mbarriers),
+    and every result must match the fp32 reference."""
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    cpu = torch.Generator().manual_seed(99)
+    for it in range(12):
+        T = 128 * int(torch.randint(1, 17, (1,), generator=cpu))
+        dh = (64, 128, 256)[int(torch.randint(0, 3, (1,), generator=cpu))]
+        B, heads = int(torch.randint(1, 5, (1,), generator=cpu)), int(torch.randint(1, 7, (1,), generator=cpu))
+        scale = (0.3, 0.8, 1.5)[it % 3]
+        q = (torch.randn(B, heads, T, dh, device="cuda", generator=gen) * scale).to(torch.bfloat16)
+        k = (torch.randn(B, heads, T, dh, device="cuda", generator=gen) * scale).to(torch.bfloat16)
+        vt = torch.randn(B, heads, dh, T, device="cuda", generator=gen).to(torch.bfloat16)
+        outs = [ops.attention(q, k, vt, impl="sm100").clone() for _ in range(4)]
+        for o in outs[1:]:
+            assert torch.equal(o, outs[0]), f"non-deterministic result at T={T} dh={dh} B={B} heads={heads}"
+        p = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()).softmax(-1)
+        ref = torch.einsum("bhts,bhds->bthd", p, vt.float()).reshape(B, T, heads * dh)
+        assert rel_err(outs[0], ref) < 2e-2, (T, dh, B, heads, scale)
+
+
+def test_conv_statistics_repeatable(ops):
+    """Same for the conv epilogue with fused statistics (halo and plain CTA-pair kernels, both granularities)."""
+    import ctypes as C
+    from advshadow_b200 import _capi as capi
+    lib = capi.lib()
+    torch.manual_seed(31)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (B, H, W, cin, cout, gran) in [(2, 8, 256, 128, 128, 4), (2, 8, 256, 128, 128, 1), (3, 32, 32, 256, 256, 4),
+                                       (1, 16, 128, 64, 256, 4)]:
+        x = torch.randn(B, H, W, cin, device="cuda").to(torch.bfloat16)
+        res = torch.randn(B, H, W, cout, device="cuda").to(torch.bfloat16)
+        wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda") / 20, torch.bfloat16)
+        bias = torch.randn(cout, device="cuda")
+        parts = lib.advs_conv_sm100_stats_parts(B, H, W)
+        results = []
+        for _ in range(3):
+            y = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device="cuda")
+            part = torch.full((B, parts, cout // gran, 2), float("nan"), device="cuda")
+            cp = capi.ConvParams()
+            cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, H, W, cout, 1, 1
+            cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), wp.data_ptr(), cin, 9
+            cp.bias, cp.out_mode, cp.y, cp.dtype, cp.residual = bias.data_ptr(), 0, y.data_ptr(), capi.BF16, res.data_ptr()
+            cp.stats_partial, cp.stats_gran = part.data_ptr(), gran
+            pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
+            capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+            capi.call("advs_conv_sm100_launch", pb.ptr, st)
+            torch.cuda.synchronize()
+            results.append((y, part))
+        for (y, part) in results[1:]:
+            assert torch.equal(y, results[0][0]) and torch.equal(part, results[0][1])
+        ref = F.conv2d(nchw(x.float()), wp.float().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2), bias, padding=1) + nchw(res.float())
+        assert rel_err(nchw(results[0][0]), ref) < 1e-2
+
+
 def test_upsample_and_edges(ops):
     torch.manual_seed(6)
     x = torch.randn(2, 5, 7, 64, device="cuda").to(torch.bfloat16)
