@@ -57,39 +57,72 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ 
 // per pixel, so the stem is a 1x1 convolution with 64 input "channels" for the implicit-GEMM kernel.
 // entry = part * 9*Cin + tap * Cin + ci; part 0 = bf16(x), part 1 = bf16(x - bf16(x)) when it fits (the fp32
 // sampler state then reaches the bf16 MMA to ~2^-17 instead of 2^-9), the rest is zero.  Zero padding of the
-// convolution = zeros here.  One thread per (pixel, 8 entries): 16-byte stores, 128 contiguous bytes per pixel.
-// CIN > 0: compile-time channel count (the divisions below fold into constants); CIN = 0: run-time Cin.
+// convolution = zeros here.
+// One thread per pixel gathers its 9*Cin inputs (lanes = consecutive pixels of a row: coalesced), the block's 256
+// rows of 128 bytes go through shared memory (144-byte pitch: conflict-free 16-byte writes) and leave as contiguous
+// 16-byte pieces, so both sides touch whole cache lines.
+// CIN > 0: compile-time channel count; CIN = 0: run-time Cin (<= 7).
+constexpr int kStemPixPerBlock = 256;
+constexpr int kStemPitch = 144;
 template <int CIN>
-__global__ void k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int H, int W, int cin_rt,
-                              int parts) {
+__global__ void __launch_bounds__(kStemPixPerBlock)
+k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int H, int W, int cin_rt, int parts) {
+  __shared__ __align__(16) uint8_t rows[kStemPixPerBlock * kStemPitch];
   const int Cin = CIN > 0 ? CIN : cin_rt;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t npix = (size_t)B * H * W;
-  if (idx >= npix * 8) return;
-  const size_t pix = idx >> 3;
-  const int chunk = (int)(idx & 7);
-  const int w0 = (int)(pix % W), h0 = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
-  const int k9 = 9 * Cin;
-  uint32_t packed[4];
+  const size_t pix0 = (size_t)blockIdx.x * kStemPixPerBlock;
+  const size_t pix = pix0 + threadIdx.x;
+  __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(rows + threadIdx.x * kStemPitch);
+  if (pix < npix) {
+    const int w0 = (int)(pix % W), h0 = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+    const int k9 = 9 * Cin;
+    if constexpr (CIN > 0) {
+      // all indices are compile-time: the row is built in registers and written with eight 16-byte stores
+      float v[9 * CIN];
 #pragma unroll
-  for (int e = 0; e < 8; e += 2) {
-    float v[2];
+      for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h0 + tap / 3 - 1, ww = w0 + tap % 3 - 1;
+        const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int slot = chunk * 8 + e + u;
-      const int part = slot / k9, r = slot - part * k9;
-      const int tap = r / Cin, ci = r - tap * Cin;
-      const int hh = h0 + tap / 3 - 1, ww = w0 + tap % 3 - 1;
-      float val = 0.f;
-      if (part < parts && hh >= 0 && hh < H && ww >= 0 && ww < W) {
-        val = __ldg(x + (((size_t)b * Cin + ci) * H + hh) * W + ww);
-        if (part == 1) val -= __bfloat162float(__float2bfloat16_rn(val));
+        for (int ci = 0; ci < CIN; ++ci)
+          v[tap * CIN + ci] = in ? __ldg(x + (((size_t)b * CIN + ci) * H + hh) * W + ww) : 0.f;
       }
-      v[u] = val;
+      float e[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) e[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9 * CIN; ++i) {
+        e[i] = v[i];
+        if (18 * CIN <= 64) e[9 * CIN + i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<uint4*>(row)[i] = make_uint4(pack_bf16x2(e[8 * i], e[8 * i + 1]), pack_bf16x2(e[8 * i + 2], e[8 * i + 3]),
+                                                      pack_bf16x2(e[8 * i + 4], e[8 * i + 5]), pack_bf16x2(e[8 * i + 6], e[8 * i + 7]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(row)[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h0 + tap / 3 - 1, ww = w0 + tap % 3 - 1;
+        const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float val = in ? __ldg(x + (((size_t)b * Cin + ci) * H + hh) * W + ww) : 0.f;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+          row[tap * Cin + ci] = hi;
+          if (parts > 1) row[k9 + tap * Cin + ci] = __float2bfloat16_rn(val - __bfloat162float(hi));
+        }
+      }
     }
-    packed[e >> 1] = pack_bf16x2(v[0], v[1]);
   }
-  *reinterpret_cast<uint4*>(col + pix * 64 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  __syncthreads();
+  // 256 rows x 8 pieces of 16 bytes, contiguous in global memory
+  uint4* dst = reinterpret_cast<uint4*>(col + pix0 * 64);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int g = it * kStemPixPerBlock + threadIdx.x;
+    const int r = g >> 3, c = g & 7;
+    if (pix0 + r < npix) dst[g] = *reinterpret_cast<const uint4*>(rows + r * kStemPitch + c * 16);
+  }
 }
 
 // matching weight rows [O][64]: both parts carry bf16(w[o][ci][tap])
@@ -382,12 +415,13 @@ int advs_pack_upconv_weight(const float* w, void* dst, int O, int I, int dtype, 
 
 int advs_stem_im2col(const float* x, void* col, int B, int H, int W, int Cin, void* stream) {
   ADVS_CHECK_ARG(x && col && B > 0 && H > 0 && W > 0 && Cin > 0 && 9 * Cin <= 64, "stem_im2col: bad args (needs 9*Cin <= 64)");
-  const size_t n = (size_t)B * H * W * 8;
-  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const size_t npix = (size_t)B * H * W;
+  const unsigned blocks = (unsigned)((npix + kStemPixPerBlock - 1) / kStemPixPerBlock);
   if (Cin == 3)
-    k_stem_im2col<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin, 2);
+    k_stem_im2col<3><<<blocks, kStemPixPerBlock, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin, 2);
   else
-    k_stem_im2col<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin, 18 * Cin <= 64 ? 2 : 1);
+    k_stem_im2col<0><<<blocks, kStemPixPerBlock, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin,
+                                                                         18 * Cin <= 64 ? 2 : 1);
   ADVS_CHECK_LAUNCH("stem_im2col");
   return ADVS_OK;
 }
