@@ -1,4 +1,4 @@
-"""Condense the two ncu exports of tests/run_gpu_ncu.sh into what profiles/ keeps:
+"""Condense the two ncu exports of tools/gpu/ncu.sh into what profiles/ keeps:
   launches_<tag>.csv (as captured)  ->  per-kernel totals of one UNet forward
   prof_<tag>_raw.csv (--page raw)   ->  prof_<tag>_key_metrics.csv + a per-kernel table."""
 import csv, re, sys, collections
