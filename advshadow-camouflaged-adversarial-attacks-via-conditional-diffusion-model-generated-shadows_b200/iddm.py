@@ -8,6 +8,7 @@ This path is the "secondary" one of the survey: it is built for parity first; it
 SIMT kernel (the tcgen05 flash kernel covers head dims 64/128/256).  CUDA only, inference only -- no fallback.
 """
 import ctypes as C
+import os
 import math
 
 import torch
@@ -17,6 +18,10 @@ from tqdm import tqdm
 from . import _capi as capi
 
 _ACT = {"silu": 1, "gelu": 2}
+
+
+# ADVS_IDDM_GRAPH=0 runs the sampling loop eagerly (debugging)
+_USE_GRAPH = os.environ.get("ADVS_IDDM_GRAPH", "1") != "0"
 
 
 def _st():
@@ -406,25 +411,79 @@ class DDIMDiffusion:
         dev = next(model.parameters()).device
         eng = model.engine(n)
         S = self.img_size
+        # ddim.py:75-84: unconditional if neither labels nor a guidance scale is given; otherwise the (possibly
+        # label-free) prediction is mixed with the unconditional one when cfg_scale > 0 (None > 0 raises there too)
+        use_labels = labels is not None
+        guided_run = False
+        if not (labels is None and cfg_scale is None):
+            if cfg_scale is None:
+                raise TypeError("'>' not supported between instances of 'NoneType' and 'int' (cfg_scale is required with labels)")
+            guided_run = use_labels and cfg_scale > 0      # without labels both predictions coincide: lerp(a, a, w) = a
         with torch.no_grad(), torch.cuda.device(dev):
-            x = (torch.randn((n, 3, S, S)) if x_T is None else x_T.float()).to(dev).contiguous()
-            coef = self._coefficients().to(dev)
-            step = torch.zeros(1, dtype=torch.int32, device=dev)
-            uncond = torch.empty_like(x)
-            guided = torch.empty_like(x)
-            for i, _ in tqdm(self.time_step, disable=None):
-                t = (torch.ones(n) * i).long().to(dev)
-                if labels is None and cfg_scale is None:
-                    eps = eng.forward(x, t)
-                else:
-                    eps = eng.forward(x, t, labels)
-                    if cfg_scale > 0:
-                        uncond.copy_(eng.forward(x, t, None))
-                        capi.call("advs_cfg_lerp", uncond.data_ptr(), eps.data_ptr(), C.c_float(float(cfg_scale)),
-                                  guided.data_ptr(), x.numel(), _st())
-                        eps = guided
+            # the sampler state IS the engine's input buffer; every per-step quantity (timestep, coefficients, step
+            # counter) is read from device memory, so one step is a fixed launch sequence: captured once per
+            # (engine, guidance mode) in a CUDA graph and replayed -- the 64x64 network is launch-latency bound
+            x = eng.x
+            x.copy_((torch.randn((n, 3, S, S)) if x_T is None else x_T.float()).to(dev))
+            if use_labels:
+                if eng.label_w is None:
+                    raise ValueError("labels given but the network was built without num_classes")
+                eng.y.copy_(labels.reshape(-1).to(device=dev, dtype=torch.int64))
+            n_steps = len(self.time_step)
+            cache = eng.__dict__.setdefault("_step_graphs", {})
+            gkey = (use_labels, guided_run)
+            st8 = cache.get(gkey)
+            if st8 is None or st8["cap"] < n_steps:
+                cap = max(n_steps, 64)
+                st8 = dict(cap=cap, coef=torch.zeros(cap, 8, dtype=torch.float32, device=dev),
+                           t=torch.zeros(cap, dtype=torch.int64, device=dev), step=torch.zeros(1, dtype=torch.int32, device=dev),
+                           cond=torch.empty_like(x), guided=torch.empty_like(x), graph=None)
+                cache[gkey] = st8
+            st8["coef"][:n_steps].copy_(self._coefficients())
+            st8["t"][:n_steps].copy_(torch.tensor([int(i) for i, _ in self.time_step], dtype=torch.int64))
+            coef, step, cond, guided = st8["coef"], st8["step"], st8["cond"], st8["guided"]
+            t_rows = st8["t"].view(torch.float32)          # [cap, 2] floats: the int64 timesteps, copied bit for bit
+            step.zero_()
+
+            def one_step():
+                st = _st()
+                capi.call("advs_select_row", t_rows.data_ptr(), 2, step.data_ptr(), eng.t.data_ptr(), n, st)
+                eng.run(use_labels)
+                eps = eng.eps
+                if guided_run:
+                    cond.copy_(eng.eps)
+                    eng.run(False)
+                    capi.call("advs_cfg_lerp", eng.eps.data_ptr(), cond.data_ptr(), C.c_float(float(cfg_scale)),
+                              guided.data_ptr(), x.numel(), st)
+                    eps = guided
                 capi.call("advs_ddim_step", x.data_ptr(), eps.data_ptr(), None, x.data_ptr(), x.numel(), coef.data_ptr(),
-                          step.data_ptr(), 1, 1, _st())
+                          step.data_ptr(), 1, 1, st)
+
+            graph = None
+            if _USE_GRAPH and n_steps > 2:
+                # the guidance scale is baked into the captured launch: one graph per scale
+                if st8["graph"] is None or st8.get("graph_scale") != (float(cfg_scale) if guided_run else None):
+                    x0 = x.clone()
+                    s = torch.cuda.Stream(device=dev)
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
+                        one_step()                 # eager once: lazy one-time kernel attribute setup
+                    torch.cuda.current_stream().wait_stream(s)
+                    x.copy_(x0)
+                    step.zero_()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        one_step()
+                    st8["graph"], st8["graph_scale"] = g, (float(cfg_scale) if guided_run else None)
+                    x.copy_(x0)
+                    step.zero_()
+                graph = st8["graph"]
+            for _ in tqdm(range(n_steps), disable=None):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    one_step()
+            x = x.clone()
             model.train()          # the reference leaves the model in train() mode (ddim.py:95)
             if return_float:
                 return x
