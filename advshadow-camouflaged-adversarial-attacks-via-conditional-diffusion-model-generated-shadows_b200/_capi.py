@@ -36,6 +36,7 @@ class ConvParams(C.Structure):
         ("dtype", C.c_int32), ("cout_valid", C.c_int32),
         ("stats_partial", C.c_void_p),
         ("up_phase", C.c_int32), ("stats_gran", C.c_int32),
+        ("y_lo", C.c_void_p),
     ]
 
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     "advs_pack_stem_weight": (C.c_int, [_vp, _vp, _i, _i, _vp]),
     "advs_conv_sm100_stats_parts": (C.c_int, [_i, _i, _i]),
     "advs_groupnorm_apply": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
+    "advs_groupnorm_apply_wide": (C.c_int, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "advs_conv_simt": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_plan": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_launch": (C.c_int, [_vp, _vp]),
@@ -78,6 +80,9 @@ SIGNATURES = {
     "advs_gaussian_blur5": (C.c_int, [_vp, _vp, _i, _i, _i, _vp]),
     "advs_shadow_composite": (C.c_int, [_vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "advs_shadow_composite_generated": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "advs_shadow_composite_generated_ex": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "advs_ddim_step_composite": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i,
+                                           _vp]),
     "advs_maxpool2x2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "advs_upsample_bilinear2x": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "advs_copy_channels": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, _vp]),

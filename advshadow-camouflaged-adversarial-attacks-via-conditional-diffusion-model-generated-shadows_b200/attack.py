@@ -53,26 +53,33 @@ def fold_candidates(flags: torch.Tensor, candidates: int) -> torch.Tensor:
     return flags.view(-1, candidates).amax(dim=1)
 
 
-def exchange_success(flags_local: torch.Tensor, group=None, pad_to: Optional[int] = None):
-    """The path's only collective.  flags_local: uint8 [B_local] on any device (NCCL on GPUs, gloo on CPU
-    in the tests).  Returns (flags_all uint8 [sum B_local], counts int64 [2] = {successes, total}).
-    Shards may be ragged: they are padded to `pad_to` (default: max over ranks) with 255 and trimmed."""
+def exchange_success(flags_local: torch.Tensor, group=None, pad_to: Optional[int] = None, counts_local=None):
+    """The path's only collective: ONE all_gather of fixed-width uint8 rows + ONE all_reduce(sum) of int64[2]
+    {successes, total} per batch, no host synchronisation.  flags_local: uint8 [B_local] on any device
+    (NCCL on GPUs, gloo on CPU in the tests).  Returns (flags_all uint8 [sum B_local], counts int64 [2]).
+    Shards may be ragged: every rank pads its row to `pad_to` with 255 (default: ceil(B_total / world) as given by
+    `shard_bounds`, i.e. the widest shard -- pass it explicitly for any other partition) and the padding is dropped
+    after the gather; 255 never is a flag value.  `counts_local`: the int64[2] that advs_success_flags already
+    produced on the device (ops.success_flags), used as is instead of being recomputed."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    counts = torch.stack([flags_local.sum(dtype=torch.int64),
-                          torch.tensor(flags_local.numel(), dtype=torch.int64, device=flags_local.device)])
+    if counts_local is None:
+        counts = torch.stack([flags_local.sum(dtype=torch.int64),
+                              torch.tensor(flags_local.numel(), dtype=torch.int64, device=flags_local.device)])
+    else:
+        counts = counts_local.to(torch.int64).clone()
     if world == 1:
         return flags_local.clone(), counts
-    n_local = torch.tensor([flags_local.numel()], dtype=torch.int64, device=flags_local.device)
-    sizes = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    width = pad_to or max(sizes)
-    padded = torch.full((width,), 255, dtype=torch.uint8, device=flags_local.device)
+    if pad_to is None:
+        raise ValueError("exchange_success: pad_to (the widest shard, e.g. ceil(B_total / world)) is required when "
+                         "world_size > 1 -- it keeps the exchange at one all_gather without a size handshake")
+    if flags_local.numel() > pad_to:
+        raise ValueError(f"exchange_success: shard of {flags_local.numel()} flags does not fit pad_to={pad_to}")
+    padded = torch.full((pad_to,), 255, dtype=torch.uint8, device=flags_local.device)
     padded[:flags_local.numel()] = flags_local
-    gathered = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
+    gathered = torch.empty(world * pad_to, dtype=torch.uint8, device=flags_local.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
     dist.all_reduce(counts, group=group)
-    return torch.cat([g[:n] for g, n in zip(gathered, sizes)]), counts
+    return gathered[gathered != 255], counts
 
 
 def victim_preprocess(images: torch.Tensor, size: int = 224) -> torch.Tensor:
@@ -87,8 +94,11 @@ class AttackLoop:
     (B_local * candidates trajectories); `victim` is any PyTorch classifier returning [N, classes] logits
     (HF models: pass `lambda x: model(x).logits`)."""
 
-    def __init__(self, sampler, victim, candidates: int = 1, victim_size: int = 224, group=None):
+    def __init__(self, sampler, victim, candidates: int = 1, victim_size: int = 224, group=None, pad_to: Optional[int] = None):
+        """`pad_to`: the widest per-rank image count (needed at world_size > 1 when shards are ragged; defaults to
+        this rank's own image count, i.e. even shards)."""
         self.sampler, self.victim, self.K, self.victim_size, self.group = sampler, victim, candidates, victim_size, group
+        self.pad_to = pad_to
 
     @torch.no_grad()
     def step(self, x_T, clean, fmask, centers, radii, labels):
@@ -98,8 +108,10 @@ class AttackLoop:
         self.sampler.set_inputs(x_T, clean, fmask, centers, radii)
         shadowed = self.sampler.run_device()
         logits = self.victim(victim_preprocess(shadowed, self.victim_size)).float()
-        flags, _ = ops.success_flags(logits, labels.to(logits.device))
-        flags = fold_candidates(flags, self.K)
-        flags_all, counts = exchange_success(flags, self.group)
+        flags, counts = ops.success_flags(logits, labels.to(logits.device))
+        if self.K > 1:                     # an image is broken if any of its candidates breaks it
+            flags = fold_candidates(flags, self.K)
+            counts = None
+        flags_all, counts = exchange_success(flags, self.group, pad_to=self.pad_to or flags.numel(), counts_local=counts)
         return {"shadowed": shadowed, "flags_local": flags, "flags": flags_all, "successes": int(counts[0]),
                 "total": int(counts[1]), "asr": float(counts[0]) / max(int(counts[1]), 1)}

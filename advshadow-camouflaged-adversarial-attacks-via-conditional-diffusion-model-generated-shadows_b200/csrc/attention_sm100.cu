@@ -382,15 +382,15 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
 
 template <int DH>
 static int attn_launch(const AttnPlan* plan, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  constexpr int slot = DH == 64 ? kOnceAttn64 : (DH == 128 ? kOnceAttn128 : kOnceAttn256);
+  if (first_use_on_device(slot)) {
     cudaError_t e = cudaFuncSetAttribute(k_attention_sm100<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          AttnCfg<DH>::smem_bytes);
     if (e != cudaSuccess) {
+      forget_first_use(slot);
       set_error("attention_sm100_launch: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ADVS_ERR_CUDA;
     }
-    attr_done = true;
   }
   dim3 grid(plan->args.T / kBQ, plan->args.B * plan->args.heads);
   k_attention_sm100<DH><<<grid, kAttnThreads, AttnCfg<DH>::smem_bytes, st>>>(plan->maps, plan->args);

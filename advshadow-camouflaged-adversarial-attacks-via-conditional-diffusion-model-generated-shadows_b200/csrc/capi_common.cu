@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace advs {
@@ -13,6 +15,31 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+constexpr int kMaxDevices = 64;
+static std::atomic<unsigned char> g_once[kOnceSlots][kMaxDevices];
+static std::atomic<int> g_sms[kMaxDevices];
+
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % kMaxDevices;
+}
+
+bool first_use_on_device(int slot) { return g_once[slot][current_device_slot()].exchange(1) == 0; }
+void forget_first_use(int slot) { g_once[slot][current_device_slot()].store(0); }
+
+int current_device_sms() {
+  const int d = current_device_slot();
+  int n = g_sms[d].load();
+  if (n <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_sms[d].store(n);
+  }
+  return n;
 }
 
 int validate_conv(const advs_conv_params* p, const char* who) {
@@ -33,6 +60,8 @@ int validate_conv(const advs_conv_params* p, const char* who) {
   ADVS_CHECK_ARG(p->up_phase == 0 || (p->stride == 1 && p->out_mode == 0 && p->nseg == 1 && !p->residual),
                  "%s: an upsample phase is a plain stride-1 NHWC convolution", who);
   ADVS_CHECK_ARG(p->dtype == ADVS_F32 || p->dtype == ADVS_BF16, "%s: bad dtype", who);
+  ADVS_CHECK_ARG(!p->y_lo || (p->out_mode == 0 && p->dtype == ADVS_BF16 && ((uintptr_t)p->y_lo % 32) == 0 && p->Cout % 32 == 0),
+                 "%s: y_lo needs out_mode 0, bf16, Cout %% 32 == 0 and a 32-byte aligned pointer", who);
   if (p->out_mode == 0) {
     ADVS_CHECK_ARG(p->y != nullptr, "%s: y is null", who);
   } else if (p->out_mode == 1) {

@@ -11,6 +11,14 @@ namespace advs {
 
 void set_error(const char* fmt, ...);
 
+// Kernel attributes (cudaFuncSetAttribute) and SM counts are per DEVICE, and one process may drive several GPUs
+// (engines are cached per device index): `first_use_on_device(slot)` is true exactly once per (slot, current device).
+enum OnceSlot { kOnceConv1Cta = 0, kOnceConv2Cta, kOnceConvHalo, kOnceAttn64, kOnceAttn128, kOnceAttn256, kOnceSelftest,
+                kOnceSlots };
+bool first_use_on_device(int slot);
+void forget_first_use(int slot);   // the attribute call failed: try again on the next launch
+int current_device_sms();          // multiProcessorCount of the current device (148 if the query fails)
+
 #define ADVS_CHECK_ARG(cond, ...)      \
   do {                                 \
     if (!(cond)) {                     \
@@ -122,6 +130,7 @@ struct EpilogueParams {
   int HW;    // pixels per image (T for attention)
   int Cout;
   int cout_valid;  // out_mode 2: real output channels
+  uint8_t* y_lo;   // out_mode 0, optional: 8 more mantissa bits per element of y ("wide" pre-norm storage)
 };
 
 inline EpilogueParams make_epilogue(const advs_conv_params& p) {
@@ -141,6 +150,7 @@ inline EpilogueParams make_epilogue(const advs_conv_params& p) {
   e.HW = p.H * p.W;
   e.Cout = p.Cout;
   e.cout_valid = (p.out_mode == 2) ? p.cout_valid : p.Cout;
+  e.y_lo = p.out_mode == 0 ? reinterpret_cast<uint8_t*>(p.y_lo) : nullptr;
   return e;
 }
 
@@ -149,6 +159,41 @@ int validate_conv(const advs_conv_params* p, const char* who);
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- "wide" pre-norm storage: bf16 + 8 mantissa-extension bits -----------------------------------
+// A tensor that is only ever read by a normalisation loses accuracy twice in bf16: once when it is stored and
+// once more when the normalised value is rounded for the GEMM.  Such tensors keep a companion int8 tensor with
+// the next 8 mantissa bits: v ~= bits(hi) + (lo << 8) as an integer add on the fp32 bit pattern -- IEEE bit
+// patterns are monotone in the magnitude, so the add carries correctly across binades and needs no exponent
+// arithmetic.  hi stays the round-to-nearest bf16 (it is also a GEMM operand and the residual); |v - decoded| <=
+// 2^-17 |v|.
+__device__ __forceinline__ int wide_lo_term(float v, uint32_t hi_bits32) {
+  // (difference in fp32 ulps, in [-2^15, 2^15]) + rounding offset, clamped so that byte 1 is the int8 to store
+  return min((int)(__float_as_uint(v) - hi_bits32) + 128, 32767);
+}
+// four consecutive values v[0..3] and their two packed bf16x2 words -> four int8 in one word
+__device__ __forceinline__ uint32_t wide_encode4(const float* v, uint32_t w01, uint32_t w23) {
+  const int t0 = wide_lo_term(v[0], w01 << 16), t1 = wide_lo_term(v[1], w01 & 0xFFFF0000u);
+  const int t2 = wide_lo_term(v[2], w23 << 16), t3 = wide_lo_term(v[3], w23 & 0xFFFF0000u);
+  return __byte_perm(__byte_perm(t0, t1, 0x0051), __byte_perm(t2, t3, 0x0051), 0x5410);
+}
+// element k (0..3) of a packed int8 word as (int)lo << 8
+template <int K>
+__device__ __forceinline__ int wide_lo_shifted(uint32_t lo4) {
+  return (int)__byte_perm(lo4, 0u, K == 0 ? 0x8804 : (K == 1 ? 0x9914 : (K == 2 ? 0xAA24 : 0xBB34)));
+}
+// 8 bf16 (uint4) + 8 int8 (uint2) -> 8 floats
+__device__ __forceinline__ void wide_decode8(const uint4& hi, const uint2& lo, float* f) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  f[0] = __uint_as_float((h[0] << 16) + wide_lo_shifted<0>(lo.x));
+  f[1] = __uint_as_float((h[0] & 0xFFFF0000u) + wide_lo_shifted<1>(lo.x));
+  f[2] = __uint_as_float((h[1] << 16) + wide_lo_shifted<2>(lo.x));
+  f[3] = __uint_as_float((h[1] & 0xFFFF0000u) + wide_lo_shifted<3>(lo.x));
+  f[4] = __uint_as_float((h[2] << 16) + wide_lo_shifted<0>(lo.y));
+  f[5] = __uint_as_float((h[2] & 0xFFFF0000u) + wide_lo_shifted<1>(lo.y));
+  f[6] = __uint_as_float((h[3] << 16) + wide_lo_shifted<2>(lo.y));
+  f[7] = __uint_as_float((h[3] & 0xFFFF0000u) + wide_lo_shifted<3>(lo.y));
 }
 
 }  // namespace advs

@@ -250,15 +250,7 @@ static int largest_divisor_leq(int n, int cap) {
   return best;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int num_sms() { return current_device_sms(); }
 
 }  // namespace advs
 
@@ -403,21 +395,20 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
 int advs_conv_sm100_launch(const void* plan_host, void* stream) {
   const ConvPlan* plan = reinterpret_cast<const ConvPlan*>(plan_host);
   ADVS_CHECK_ARG(plan && plan->magic == 0xC0A7B200u, "conv_sm100_launch: not a plan");
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (plan->halo) return launch_conv_2cta_halo(plan, (cudaStream_t)stream);
+  if (plan->two_cta) return launch_conv_2cta(plan, (cudaStream_t)stream);
+  if (first_use_on_device(kOnceConv1Cta)) {
     cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg<128>::smem_bytes);
     cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      forget_first_use(kOnceConv1Cta);
       set_error("conv_sm100_launch: cudaFuncSetAttribute failed: %s",
                 cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       return ADVS_ERR_CUDA;
     }
-    attr_done = true;
   }
-  if (plan->halo) return launch_conv_2cta_halo(plan, (cudaStream_t)stream);
-  if (plan->two_cta) return launch_conv_2cta(plan, (cudaStream_t)stream);
   if (plan->bn == 256)
     k_conv_sm100<256><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);
   else

@@ -218,17 +218,16 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
 uint32_t conv_2cta_smem_bytes(int bn) { return bn == 256 ? ConvCfg2<256>::smem_bytes : ConvCfg2<128>::smem_bytes; }
 
 int launch_conv_2cta(const ConvPlan* plan, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (first_use_on_device(kOnceConv2Cta)) {
     cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg2<128>::smem_bytes);
     cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg2<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_error("conv_sm100_launch(2cta): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      forget_first_use(kOnceConv2Cta);
       return ADVS_ERR_CUDA;
     }
-    attr_done = true;
   }
   if (plan->bn == 256)
     k_conv_sm100_2cta<256><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);

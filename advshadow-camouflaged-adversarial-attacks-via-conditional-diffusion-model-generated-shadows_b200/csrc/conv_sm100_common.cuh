@@ -109,13 +109,19 @@ __device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, cons
 __device__ __forceinline__ void epilogue_write32(const EpilogueParams& e, const float* v, size_t m, int b, int t, int n) {
   if (e.out_mode == 0) {
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n;
+    uint32_t lo8[8];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       uint32_t o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
       st_global_256(yp + 16 * j, o);
+      if (e.y_lo) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lo8[4 * j + i] = wide_encode4(v + 16 * j + 4 * i, o[2 * i], o[2 * i + 1]);
+      }
     }
+    if (e.y_lo) st_global_256(e.y_lo + m * e.Cout + n, lo8);   // 32 channels x int8
   } else if (e.out_mode == 2) {
     float* dst = reinterpret_cast<float*>(e.y) + ((size_t)b * e.cout_valid + n) * e.HW + t;
 #pragma unroll

@@ -274,17 +274,16 @@ namespace advs {
 uint32_t conv_2cta_halo_smem_bytes(int bn) { return bn == 256 ? ConvCfgH<256>::smem_bytes : ConvCfgH<128>::smem_bytes; }
 
 int launch_conv_2cta_halo(const ConvPlan* plan, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (first_use_on_device(kOnceConvHalo)) {
     cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfgH<128>::smem_bytes);
     cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfgH<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_error("conv_sm100_launch(halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      forget_first_use(kOnceConvHalo);
       return ADVS_ERR_CUDA;
     }
-    attr_done = true;
   }
   if (plan->bn == 256)
     k_conv_sm100_2cta_halo<256><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);

@@ -294,8 +294,9 @@ __global__ void k_upsample2x(const T* __restrict__ x, T* __restrict__ y, int B, 
 
 // ---------------------------------------------------------------------------------------
 // K8. DDIM update in the reference's exact fp32 operation order (dm1:457-472).
-__global__ void k_ddim_step(const float* __restrict__ x, const float* __restrict__ eps,
-                            const float* __restrict__ noise, float* __restrict__ out, size_t n,
+// x and out may alias (the samplers update the state in place): no __restrict__ on either.
+__global__ void k_ddim_step(const float* x, const float* __restrict__ eps,
+                            const float* __restrict__ noise, float* out, size_t n,
                             const float* __restrict__ coef, const int32_t* __restrict__ step_dev, int clip) {
   const float* c = coef + 8 * (size_t)(*step_dev);
   const float s1 = c[0], sa = c[1], sp = c[2], cdir = c[3], sigma = c[4];
@@ -335,8 +336,8 @@ __global__ void k_ddim_step(const float* __restrict__ x, const float* __restrict
 }
 
 // DDPM ancestral step (dm1:356-395): x0 = c0*x - c1*eps; clamp; mean = c2*x0 + c3*x; + c4*z
-__global__ void k_ddpm_step(const float* __restrict__ x, const float* __restrict__ eps,
-                            const float* __restrict__ noise, float* __restrict__ out, size_t n,
+__global__ void k_ddpm_step(const float* x, const float* __restrict__ eps,
+                            const float* __restrict__ noise, float* out, size_t n,
                             const float* __restrict__ coef, const int32_t* __restrict__ step_dev, int clip) {
   const float* c = coef + 8 * (size_t)(*step_dev);
   const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];

@@ -12,7 +12,14 @@ __device__ __forceinline__ void epilogue_store1(const EpilogueParams& e, size_t 
   if (e.temb) v += e.temb[(size_t)b * e.temb_stride + n];
   if (e.out_mode == 0) {
     if (e.residual) v += to_f(reinterpret_cast<const T*>(e.residual)[m * e.Cout + n]);
-    reinterpret_cast<T*>(e.y)[m * e.Cout + n] = from_f<T>(v);
+    const T hv = from_f<T>(v);
+    reinterpret_cast<T*>(e.y)[m * e.Cout + n] = hv;
+    if constexpr (sizeof(T) == 2) {
+      if (e.y_lo) {   // "wide" pre-norm storage, see common.cuh
+        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hv) << 16;
+        e.y_lo[m * e.Cout + n] = (uint8_t)((uint32_t)wide_lo_term(v, hb) >> 8);
+      }
+    }
   } else if (e.out_mode == 2) {
     if (n < e.cout_valid) reinterpret_cast<float*>(e.y)[((size_t)b * e.cout_valid + n) * e.HW + t] = v;
   } else {

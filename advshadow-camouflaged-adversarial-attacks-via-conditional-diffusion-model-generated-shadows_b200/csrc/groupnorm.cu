@@ -28,6 +28,19 @@ static GnGeom gn_geom(int B, int HW) {
   return g;
 }
 
+// Geometry of the statistics pass.  It depends on the image size ONLY: the fp32 partial sums are then formed in the
+// same order whatever the batch size, so an image's result does not depend on which batch (or sub-batch of a
+// multi-stream sampler) it is processed in -- trajectories are bit-reproducible across batch sizes.
+static GnGeom gn_geom_stats(int HW) {
+  int chunks = (HW + 1023) / 1024;          // ~1024 pixels per chunk, at most 64 chunks per image
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  GnGeom g;
+  g.pix_per_chunk = (HW + chunks - 1) / chunks;
+  g.chunks = (HW + g.pix_per_chunk - 1) / g.pix_per_chunk;
+  return g;
+}
+
 // part layout: [B][chunks][Ctot][2]
 template <typename T>
 __global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot, int HW, int pix_per_chunk,
@@ -160,9 +173,10 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ p
 
 // thread = one 8-channel vector position, looping over the pixels of its chunk: the 16 scale/shift
 // floats stay in registers, so the stream is exactly one 16-byte load + one 16-byte store per vector.
-template <typename T, bool SILU>
+template <typename T, bool SILU, bool WIDE = false>
 __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict__ x1, int c1, int HW,
-                           int pix_per_chunk, const float* __restrict__ scale_shift, T* __restrict__ y) {
+                           int pix_per_chunk, const float* __restrict__ scale_shift, T* __restrict__ y,
+                           const uint8_t* __restrict__ lo0 = nullptr, const uint8_t* __restrict__ lo1 = nullptr) {
   const int Ctot = c0 + c1;
   const int cv = Ctot / 8;
   const int ppi = blockDim.x / cv;
@@ -187,9 +201,24 @@ __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict
   const T* src = first ? x0 + ((size_t)b * HW) * c0 + c : x1 + ((size_t)b * HW) * c1 + (c - c0);
   const int cs = first ? c0 : c1;
   T* dst = y + ((size_t)b * HW) * Ctot + c;
-  auto body = [&](const Vec8<T>& vin, int p) {
+  // "wide" sources carry 8 more mantissa bits per element in a companion int8 tensor (common.cuh)
+  const uint8_t* lsrc = nullptr;
+  if constexpr (WIDE) {
+    const uint8_t* l = first ? lo0 : lo1;
+    if (l) lsrc = first ? l + ((size_t)b * HW) * c0 + c : l + ((size_t)b * HW) * c1 + (c - c0);
+  }
+  auto load_lo = [&](int p) {
+    uint2 r = make_uint2(0u, 0u);
+    if constexpr (WIDE) {
+      if (lsrc)
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(lsrc + (size_t)p * cs));
+    }
+    return r;
+  };
+  auto body = [&](const Vec8<T>& vin, uint2 lo, int p) {
     float f[8];
-    vin.to_float(f);
+    if constexpr (WIDE && sizeof(T) == 2) wide_decode8(vin.v, lo, f);
+    else vin.to_float(f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float a = fmaf(f[i], sc[i], sh[i]);
@@ -206,21 +235,25 @@ __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict
   int p = p0 + pl;
   for (; p + 7 * ppi < p1; p += 8 * ppi) {   // 8 independent 16-byte loads in flight per thread
     Vec8<T> v[8];
+    uint2 l[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u].load_stream(src + (size_t)(p + u * ppi) * cs);
+    for (int u = 0; u < 8; ++u) {
+      v[u].load_stream(src + (size_t)(p + u * ppi) * cs);
+      l[u] = load_lo(p + u * ppi);
+    }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) body(v[u], p + u * ppi);
+    for (int u = 0; u < 8; ++u) body(v[u], l[u], p + u * ppi);
   }
   for (; p < p1; p += ppi) {
     Vec8<T> v;
     v.load_stream(src + (size_t)p * cs);
-    body(v, p);
+    body(v, load_lo(p), p);
   }
 }
 
 template <typename T>
 static int gn_partial_impl(const void* x, int C, int B, int HW, float* part, cudaStream_t st) {
-  GnGeom g = gn_geom(B, HW);
+  GnGeom g = gn_geom_stats(HW);
   int cv = C / 8;
   int threads = cv <= 256 ? 256 : 1024;
   int ppi = threads / cv;
@@ -243,7 +276,7 @@ static int gn_finalize_impl(const float* part0, int c0, int parts0, int gran0, c
 template <typename T>
 static int gn_stats_impl(const void* x0, int c0, const void* x1, int c1, int B, int HW, int groups, float eps,
                          const float* gamma, const float* beta, float* scale_shift, void* ws, cudaStream_t st) {
-  GnGeom g = gn_geom(B, HW);
+  GnGeom g = gn_geom_stats(HW);
   float* p0 = (float*)ws;
   float* p1 = p0 + (size_t)B * g.chunks * c0 * 2;
   int rc = gn_partial_impl<T>(x0, c0, B, HW, p0, st);
@@ -271,6 +304,23 @@ static int gn_apply_impl(const void* x0, int c0, const void* x1, int c1, int B, 
   return ADVS_OK;
 }
 
+static int gn_apply_wide_impl(const void* x0, const void* lo0, int c0, const void* x1, const void* lo1, int c1, int B, int HW,
+                              const float* ss, int silu, void* y, cudaStream_t st) {
+  using T = __nv_bfloat16;
+  GnGeom g = gn_geom(B, HW);
+  int cv = (c0 + c1) / 8;
+  int threads = cv <= 256 ? 256 : 1024;
+  dim3 grid(g.chunks, B);
+  if (silu)
+    k_gn_apply<T, true, true><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y,
+                                                        (const uint8_t*)lo0, (const uint8_t*)lo1);
+  else
+    k_gn_apply<T, false, true><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y,
+                                                         (const uint8_t*)lo0, (const uint8_t*)lo1);
+  ADVS_CHECK_LAUNCH("groupnorm_apply_wide");
+  return ADVS_OK;
+}
+
 }  // namespace advs
 
 using namespace advs;
@@ -279,7 +329,7 @@ extern "C" {
 
 size_t advs_groupnorm_workspace_bytes(int B, int HW, int C) {
   if (B <= 0 || HW <= 0 || C <= 0) return 0;
-  GnGeom g = gn_geom(B, HW);
+  GnGeom g = gn_geom_stats(HW);
   return (size_t)B * g.chunks * C * 2 * sizeof(float);
 }
 
@@ -302,7 +352,7 @@ int advs_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int B, 
 
 int advs_groupnorm_partial_parts(int B, int HW) {
   if (B <= 0 || HW <= 0) return 0;
-  return gn_geom(B, HW).chunks;
+  return gn_geom_stats(HW).chunks;
 }
 
 int advs_groupnorm_partial(const void* x, int C, int B, int HW, float* part, int dtype, void* stream) {
@@ -344,6 +394,18 @@ int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, 
   if (dtype == ADVS_F32) return gn_apply_impl<float>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
   if (dtype == ADVS_BF16) return gn_apply_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
   ADVS_CHECK_ARG(false, "groupnorm_apply: bad dtype");
+}
+
+int advs_groupnorm_apply_wide(const void* x0, const void* lo0, int c0, const void* x1, const void* lo1, int c1, int B,
+                              int HW, const float* scale_shift, int silu, void* y, void* stream) {
+  ADVS_CHECK_ARG(x0 && c0 > 0 && B > 0 && HW > 0 && scale_shift && y, "groupnorm_apply_wide: bad args");
+  if (!x1) { c1 = 0; lo1 = nullptr; }
+  ADVS_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm_apply_wide: channel counts must be multiples of 8");
+  ADVS_CHECK_ARG((c0 + c1) / 8 <= 1024, "groupnorm_apply_wide: at most 8192 channels");
+  ADVS_CHECK_ARG(((uintptr_t)lo0 | (uintptr_t)lo1) % 8 == 0, "groupnorm_apply_wide: lo pointers must be 8-byte aligned");
+  if (!lo0 && !lo1)
+    return gn_apply_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
+  return gn_apply_wide_impl(x0, lo0, c0, x1, lo1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -64,11 +64,8 @@ __global__ void __launch_bounds__(128, 1) k_selftest_umma_row_shift(int r0, int 
 extern "C" int advs_selftest_umma_row_shift(int r0, int base_offset_mode, float* out, void* stream) {
   ADVS_CHECK_ARG(out && r0 >= 0 && r0 <= 140, "selftest_umma_row_shift: bad args");
   const int smem = 272 * 128 + 64 * 128 + 64 + 1024;
-  static bool done = false;
-  if (!done) {
+  if (advs::first_use_on_device(advs::kOnceSelftest))
     cudaFuncSetAttribute(advs::k_selftest_umma_row_shift, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    done = true;
-  }
   advs::k_selftest_umma_row_shift<<<1, 128, smem, (cudaStream_t)stream>>>(r0, base_offset_mode, out);
   ADVS_CHECK_LAUNCH("selftest_umma_row_shift");
   return ADVS_OK;

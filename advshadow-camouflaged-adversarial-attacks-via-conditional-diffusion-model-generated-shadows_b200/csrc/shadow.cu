@@ -78,25 +78,125 @@ __global__ void k_shadow_composite(const float* __restrict__ img, const float* _
   }
 }
 
-__global__ void k_shadow_composite_generated(const float* __restrict__ img, const float* __restrict__ xfin,
-                                             const float* __restrict__ centers, const float* __restrict__ radii,
-                                             const float* __restrict__ fmask, int Cm, float* __restrict__ out, int B,
-                                             int C, int H, int W) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t hw = (size_t)H * W;
-  size_t n = (size_t)B * C * hw;
-  if (i >= n) return;
-  size_t pix = i % hw;
-  int w = (int)(pix % W), h = (int)(pix / W);
-  int c = (int)((i / hw) % C);
-  int b = (int)(i / (hw * C));
-  float sm = disk_mask_value(w, h, centers[2 * b], centers[2 * b + 1], radii[b]);
-  float fm = fmask[((size_t)b * Cm + (Cm == 1 ? 0 : c)) * hw + pix];
-  float m = __fmul_rn(sm, fm);
-  float x = img[i];
-  float keep = __fmul_rn(x, __fsub_rn(1.f, m));
-  float g = clamp01(xfin[i]);  // np.clip(generated, 0, 1), main.py:135
-  out[i] = clamp01(__fadd_rn(keep, __fmul_rn(g, m)));
+// Fused tail of the shadow sampler (one pass over the images instead of update + mask + [blur] + composite):
+//   x'  = DDIM update of the last step (dm1:457-472; skipped when eps == nullptr: x is then already final)
+//   m   = disk(centre, radius) [5x5 Gaussian-blurred: ts:147-153, 244-247 / dt:851-854] * feature_mask
+//   out = clamp(img*(1-m) + clip(x',0,1)*m, 0, 1)                                        (dm2:650-653)
+// One thread per VEC consecutive pixels of a row and all channels: the mask is built once per pixel, the images move
+// as 16-byte vectors, indices are 32-bit.  Every value is formed in the reference's fp32 operation order (the
+// blurred {0,1} mask is a sum of dyadic rationals, exact in any order), so the result is bit-identical to the
+// separate kernels above.  x and x_out may alias.
+template <int VEC, bool BLUR>
+__global__ void k_ddim_final_composite(const float* x, const float* __restrict__ eps, float* x_out,
+                                       const float* __restrict__ coef, const int32_t* __restrict__ step_dev, int clip,
+                                       const float* __restrict__ img, const float* __restrict__ centers,
+                                       const float* __restrict__ radii, const float* __restrict__ fmask, int Cm,
+                                       float* __restrict__ out, int C, int H, int W) {
+  const int b = blockIdx.y;
+  const int wq = W / VEC;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * wq) return;
+  const int h = q / wq, w0 = (q - h * wq) * VEC;
+  const float c0 = centers[2 * b], c1 = centers[2 * b + 1], r = radii[b];
+  float sm[VEC];
+  if (BLUR) {
+    const float kw[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+    int wx[VEC + 4];
+#pragma unroll
+    for (int i = 0; i < VEC + 4; ++i) wx[i] = reflect101(w0 + i - 2, W);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+      const int hy = reflect101(h + dy - 2, H);
+      float d[VEC + 4];
+#pragma unroll
+      for (int i = 0; i < VEC + 4; ++i) d[i] = disk_mask_value(wx[i], hy, c0, c1, r);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float row = 0.f;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) row = __fadd_rn(row, __fmul_rn(kw[dx], d[k + dx]));
+        acc[k] = __fadd_rn(acc[k], __fmul_rn(kw[dy], row));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) sm[k] = acc[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) sm[k] = disk_mask_value(w0 + k, h, c0, c1, r);
+  }
+  float s1 = 0.f, sa = 1.f, sp = 1.f, cdir = 0.f;
+  if (eps) {
+    const float* cf = coef + 8 * (size_t)(*step_dev);
+    s1 = cf[0]; sa = cf[1]; sp = cf[2]; cdir = cf[3];
+  }
+  const size_t hw = (size_t)H * W;
+  const size_t pix = (size_t)h * W + w0;
+  float fm[VEC];
+  for (int c = 0; c < C; ++c) {
+    const size_t i = ((size_t)b * C + c) * hw + pix;
+    float xv[VEC], ev[VEC], iv[VEC], ov[VEC];
+    if (c == 0 || Cm != 1) {
+      const float* fp = fmask + ((size_t)b * Cm + (Cm == 1 ? 0 : c)) * hw + pix;
+      if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(fp); fm[0] = t.x; fm[1] = t.y; fm[2] = t.z; fm[3] = t.w; }
+      else fm[0] = fp[0];
+    }
+    if (VEC == 4) {
+      float4 t = *reinterpret_cast<const float4*>(x + i);
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      t = *reinterpret_cast<const float4*>(img + i);
+      iv[0] = t.x; iv[1] = t.y; iv[2] = t.z; iv[3] = t.w;
+      if (eps) { t = *reinterpret_cast<const float4*>(eps + i); ev[0] = t.x; ev[1] = t.y; ev[2] = t.z; ev[3] = t.w; }
+    } else {
+      xv[0] = x[i]; iv[0] = img[i];
+      if (eps) ev[0] = eps[i];
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float xf = xv[k];
+      if (eps) {
+        float x0 = __fdiv_rn(__fsub_rn(xv[k], __fmul_rn(s1, ev[k])), sa);
+        if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        xf = __fadd_rn(__fmul_rn(sp, x0), __fmul_rn(cdir, ev[k]));   // sigma = 0 on this path (eta = 0)
+        xv[k] = xf;
+      }
+      const float m = __fmul_rn(sm[k], fm[k]);
+      const float keep = __fmul_rn(iv[k], __fsub_rn(1.f, m));
+      ov[k] = clamp01(__fadd_rn(keep, __fmul_rn(clamp01(xf), m)));
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(out + i) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      if (eps) *reinterpret_cast<float4*>(x_out + i) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+    } else {
+      out[i] = ov[0];
+      if (eps) x_out[i] = xv[0];
+    }
+  }
+}
+
+__global__ void k_advance_step_s(int32_t* step_dev, int advance) { *step_dev += advance; }
+
+static int launch_final_composite(const float* x, const float* eps, float* x_out, const float* coef, int32_t* step_dev,
+                                  int advance, int clip, const float* img, const float* centers, const float* radii,
+                                  const float* fmask, int Cm, int blur, float* out, int B, int C, int H, int W,
+                                  cudaStream_t st, const char* who) {
+  const bool vec = W % 4 == 0 && (((uintptr_t)x | (uintptr_t)eps | (uintptr_t)x_out | (uintptr_t)img | (uintptr_t)fmask |
+                                   (uintptr_t)out) % 16) == 0;
+  const int quads = H * (vec ? W / 4 : W);
+  dim3 grid((quads + 127) / 128, B);
+#define ADVS_FC(V, BL) k_ddim_final_composite<V, BL><<<grid, 128, 0, st>>>(x, eps, x_out, coef, step_dev, clip, img, centers, \
+                                                                          radii, fmask, Cm, out, C, H, W)
+  if (vec) { if (blur) ADVS_FC(4, true); else ADVS_FC(4, false); }
+  else { if (blur) ADVS_FC(1, true); else ADVS_FC(1, false); }
+#undef ADVS_FC
+  ADVS_CHECK_LAUNCH(who);
+  if (eps && advance) {
+    k_advance_step_s<<<1, 1, 0, st>>>(step_dev, advance);
+    ADVS_CHECK_LAUNCH(who);
+  }
+  return ADVS_OK;
 }
 
 __global__ void k_success_flags(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B,
@@ -109,7 +209,7 @@ __global__ void k_success_flags(const float* __restrict__ logits, const int64_t*
     float bv = l[0];
     for (int c = 1; c < classes; ++c) {
       float v = l[c];
-      if (v > bv) { bv = v; best = c; }
+      if (v > bv || (v != v && bv == bv)) { bv = v; best = c; }   // torch.max: the first NaN wins and sticks
     }
     ok = ((int64_t)best != labels[b]) ? 1 : 0;
     flags[b] = (uint8_t)ok;
@@ -156,16 +256,30 @@ int advs_shadow_composite(const float* img, const float* shadow_mask, const floa
   return ADVS_OK;
 }
 
+int advs_shadow_composite_generated_ex(const float* img, const float* x_final, const float* centers, const float* radii,
+                                       const float* feature_mask, int Cm, int blur, float* out, int B, int C, int H, int W,
+                                       void* stream) {
+  ADVS_CHECK_ARG(img && x_final && centers && radii && feature_mask && out, "shadow_composite_generated: null pointer");
+  ADVS_CHECK_ARG(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0 && (Cm == 1 || Cm == C), "shadow_composite_generated: bad shape");
+  return launch_final_composite(x_final, nullptr, nullptr, nullptr, nullptr, 0, 0, img, centers, radii, feature_mask, Cm, blur,
+                                out, B, C, H, W, (cudaStream_t)stream, "shadow_composite_generated");
+}
+
 int advs_shadow_composite_generated(const float* img, const float* x_final, const float* centers, const float* radii,
                                     const float* feature_mask, int Cm, float* out, int B, int C, int H, int W,
                                     void* stream) {
-  ADVS_CHECK_ARG(img && x_final && centers && radii && feature_mask && out, "shadow_composite_generated: null pointer");
-  ADVS_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && (Cm == 1 || Cm == C), "shadow_composite_generated: bad shape");
-  size_t n = (size_t)B * C * H * W;
-  k_shadow_composite_generated<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      img, x_final, centers, radii, feature_mask, Cm, out, B, C, H, W);
-  ADVS_CHECK_LAUNCH("shadow_composite_generated");
-  return ADVS_OK;
+  return advs_shadow_composite_generated_ex(img, x_final, centers, radii, feature_mask, Cm, 0, out, B, C, H, W, stream);
+}
+
+int advs_ddim_step_composite(const float* x, const float* eps, float* x_out, const float* coef, int32_t* step_dev,
+                             int advance, int clip_denoised, const float* img, const float* centers, const float* radii,
+                             const float* feature_mask, int Cm, int blur, float* out, int B, int C, int H, int W,
+                             void* stream) {
+  ADVS_CHECK_ARG(x && eps && x_out && coef && step_dev, "ddim_step_composite: null sampler pointer");
+  ADVS_CHECK_ARG(img && centers && radii && feature_mask && out, "ddim_step_composite: null composite pointer");
+  ADVS_CHECK_ARG(B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0 && (Cm == 1 || Cm == C), "ddim_step_composite: bad shape");
+  return launch_final_composite(x, eps, x_out, coef, step_dev, advance, clip_denoised, img, centers, radii, feature_mask, Cm,
+                                blur, out, B, C, H, W, (cudaStream_t)stream, "ddim_step_composite");
 }
 
 int advs_success_flags(const float* logits, const int64_t* labels, int B, int classes, uint8_t* flags,

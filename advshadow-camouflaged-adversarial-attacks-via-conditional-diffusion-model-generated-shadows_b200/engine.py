@@ -27,7 +27,13 @@ class UNetEngine:
 
     def __init__(self, spec: UNetSpec, params: Dict[str, torch.Tensor], B: int, H: int, W: int,
                  precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto", fuse_gn_stats: bool = True,
-                 fuse_upsample: bool = True):
+                 fuse_upsample: bool = True, wide_prenorm: int = 2):
+        """`wide_prenorm`: bf16 mode only -- tensors of the `wide_prenorm` highest-resolution levels that a GroupNorm
+        reads (residual stream, conv1 outputs, skips) are stored as bf16 + an int8 mantissa extension
+        (advs_conv_params.y_lo), so the value entering the normalisation carries 16 mantissa bits like the
+        reference's fp32 tensor (dm1:71-72, 83-84) and the GEMM operand is rounded once instead of twice.  These
+        levels have the fewest channels per dot product, hence the least averaging of rounding noise: the error
+        study in DESIGN.md attributes 90 % of the bf16-mode output variance to them.  0 disables."""
         if precision not in _DT:
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         any_p = next(iter(params.values()))
@@ -93,6 +99,27 @@ class UNetEngine:
                 name = plan.new_buf("gnpart", (B, parts, a["cout"] // gran, 2), "f32")
                 plan.bufs[name].first, plan.bufs[name].last = idx, plan.bufs[a["dst"]].last
                 self._stat_buf[a["dst"]] = (name, parts, gran)
+        # "wide" pre-norm storage: an int8 companion (same lifetime) for every conv output of the top levels
+        # that a GroupNorm reads
+        self._lo_buf = {}
+        self.wide_prenorm = wide_prenorm if precision == "bf16" else 0
+        if self.wide_prenorm > 0:
+            for idx, op in enumerate(plan.ops):
+                a = op.args
+                if op.kind == "stem":
+                    if not self._stem_sm100_ok(a):
+                        continue
+                elif op.kind == "upconv":
+                    pass
+                elif not (op.kind == "conv" and a["qkv"] is None):
+                    continue
+                dst = a["dst"]
+                shp = plan.shape(dst)
+                if dst not in gn_inputs or shp[3] % 32 or shp[1] << self.wide_prenorm <= H:
+                    continue
+                name = plan.new_buf("lo8", shp, "u8")
+                plan.bufs[name].first, plan.bufs[name].last = idx, plan.bufs[dst].last
+                self._lo_buf[dst] = name
         plan.assign_offsets(self.act_bytes)
 
         dev = self.device
@@ -141,8 +168,8 @@ class UNetEngine:
     def buffer_view(self, buf):
         """torch view of an arena buffer (debug / tests)."""
         b = self.plan.bufs[buf]
-        dt = _TORCH_DT[self.precision] if b.kind == "act" else torch.float32
-        n = b.elems * (self.act_bytes if b.kind == "act" else 4)
+        dt = {"act": _TORCH_DT[self.precision], "f32": torch.float32, "u8": torch.int8}[b.kind]
+        n = b.elems * {"act": self.act_bytes, "f32": 4, "u8": 1}[b.kind]
         return self.arena[b.offset:b.offset + n].view(dt).view(*[s for s in b.shape if not isinstance(s, str)])
 
     # ---- static allocations that depend only on shapes ----
@@ -176,19 +203,34 @@ class UNetEngine:
         ted = spec.time_embed_dim
         self.temb_w = torch.empty(self.plan.temb_total, ted, dtype=torch.float32, device=dev)
         self.temb_b = torch.empty(self.plan.temb_total, dtype=torch.float32, device=dev)
+        mc = spec.model_channels
+        self.te0_w = torch.empty(ted, mc, dtype=torch.float32, device=dev)
+        self.te0_b = torch.empty(ted, dtype=torch.float32, device=dev)
+        self.te2_w = torch.empty(ted, ted, dtype=torch.float32, device=dev)
+        self.te2_b = torch.empty(ted, dtype=torch.float32, device=dev)
+        # GroupNorm affine parameters live in engine-owned storage too: their addresses are baked into the launch
+        # list and into captured CUDA graphs, which therefore stay valid across load_weights()
+        self._gn = {}
+        for op in self.plan.ops:
+            if op.kind == "gn" and op.args["weight"] not in self._gn:
+                c = op.args["C"]
+                self._gn[op.args["weight"]] = (torch.empty(c, dtype=torch.float32, device=dev),
+                                               torch.empty(c, dtype=torch.float32, device=dev))
+        self.weights_version = 0
 
     # ---- weights ----
     def load_weights(self, params: Dict[str, torch.Tensor]):
-        """(Re)pack every parameter into the kernels' layouts.  Pointers stay fixed, so launch plans
-        and captured CUDA graphs remain valid after a reload."""
+        """(Re)pack every parameter into engine-owned buffers in the kernels' layouts.  No kernel argument ever
+        points at a parameter tensor, so launch plans and captured CUDA graphs remain valid after a reload -- even
+        when the parameters' storage moved (`load_state_dict(assign=True)`, `p.data = ...`).  Temporaries made here
+        are consumed on the current stream and released by torch's stream-ordered allocator."""
         st = _stream_ptr()
-        self._params = {k: v.detach() for k, v in params.items()}
+        src = {k: v.detach() for k, v in params.items()}
 
         def p32(name):
-            t = self._params[name]
+            t = src[name]
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
-                self._keep.append(t)
             return t
 
         with torch.cuda.device(self.device):
@@ -206,7 +248,6 @@ class UNetEngine:
                 O, I, kh, kw = w.shape          # dst may have more (zero) rows than O: the padded head
                 dt = capi.F32 if dst.dtype == torch.float32 else capi.BF16
                 capi.call("advs_pack_conv_weight", w.data_ptr(), dst.data_ptr(), O, I, kh, kw, dt, st)
-                self._keep.append(w)
             for names, dst in self._bias.items():
                 acc = p32(names[0] + ".bias").clone()
                 for n in names[1:]:
@@ -217,17 +258,15 @@ class UNetEngine:
                 self.temb_w[off:off + slot.cout].copy_(p32(slot.weight + ".weight"))
                 self.temb_b[off:off + slot.cout].copy_(p32(slot.weight + ".bias"))
                 off += slot.cout
-            self.te0_w, self.te0_b = p32("time_embed.0.weight"), p32("time_embed.0.bias")
-            self.te2_w, self.te2_b = p32("time_embed.2.weight"), p32("time_embed.2.bias")
-            self._gn = {}
-            for op in self.plan.ops:
-                if op.kind == "gn":
-                    n = op.args["weight"]
-                    self._gn[n] = (p32(n + ".weight"), p32(n + ".bias"))
-        if self._weights_loaded:
-            # GroupNorm affine pointers are baked into the launch list
-            self._build_launches()
+            self.te0_w.copy_(p32("time_embed.0.weight"))
+            self.te0_b.copy_(p32("time_embed.0.bias"))
+            self.te2_w.copy_(p32("time_embed.2.weight"))
+            self.te2_b.copy_(p32("time_embed.2.bias"))
+            for n, (g, bt) in self._gn.items():
+                g.copy_(p32(n + ".weight"))
+                bt.copy_(p32(n + ".bias"))
         self._weights_loaded = True
+        self.weights_version += 1
 
     # ---- launch list ----
     def _build_launches(self):
@@ -249,6 +288,8 @@ class UNetEngine:
                 if a["dst"] in self._stat_buf:
                     cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
                     cp.stats_gran = self._stat_buf[a["dst"]][2]
+                if a["dst"] in self._lo_buf:
+                    cp.y_lo = self._ptr(self._lo_buf[a["dst"]])
                 self._keep.append(cp)
                 pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
                 with torch.cuda.device(self.device):
@@ -300,8 +341,13 @@ class UNetEngine:
                 L.append((lib.advs_groupnorm_finalize_ex, (parts[0][0], c0, parts[0][1], parts[0][2], p1, c1, n1, g1, B, a["HW"],
                                                            a["groups"], 1e-5, g.data_ptr(), bt.data_ptr(), self._ptr(a["ss"])),
                           "gn_finalize"))
-                L.append((lib.advs_groupnorm_apply, (x0, c0, x1, c1, B, a["HW"], self._ptr(a["ss"]),
-                                                     1 if a["silu"] else 0, self._ptr(a["dst"]), dt), "gn_apply"))
+                los = [self._ptr(self._lo_buf[sn]) if sn in self._lo_buf else None for sn in srcs] + [None]
+                if los[0] or los[1]:
+                    L.append((lib.advs_groupnorm_apply_wide, (x0, los[0], c0, x1, los[1], c1, B, a["HW"], self._ptr(a["ss"]),
+                                                              1 if a["silu"] else 0, self._ptr(a["dst"])), "gn_apply"))
+                else:
+                    L.append((lib.advs_groupnorm_apply, (x0, c0, x1, c1, B, a["HW"], self._ptr(a["ss"]),
+                                                         1 if a["silu"] else 0, self._ptr(a["dst"]), dt), "gn_apply"))
                 self.n_kernels += 2
             elif op.kind == "conv":
                 cp = capi.ConvParams()
@@ -328,6 +374,8 @@ class UNetEngine:
                 if a["dst"] in self._stat_buf:
                     cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
                     cp.stats_gran = self._stat_buf[a["dst"]][2]
+                if a["dst"] in self._lo_buf:
+                    cp.y_lo = self._ptr(self._lo_buf[a["dst"]])
                 self._keep.append(cp)
                 if self._conv_sm100_ok(a):
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
@@ -363,6 +411,8 @@ class UNetEngine:
                     if a["dst"] in self._stat_buf:
                         cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
                         cp.stats_gran = self._stat_buf[a["dst"]][2]
+                    if a["dst"] in self._lo_buf:
+                        cp.y_lo = self._ptr(self._lo_buf[a["dst"]])
                     self._keep.append(cp)
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
                     with torch.cuda.device(self.device):
@@ -441,13 +491,15 @@ class UNetEngine:
                     if sname not in self._stat_buf:
                         out.append(("gn_stats", 0, self.B * a["HW"] * plan.shape(sname)[3] * ab))   # one read
                 out.append(("gn_finalize", 0, 0))
-                out.append(("gn_apply", 0, 2 * n * ab))              # one read + one write
+                wide = sum(self.B * a["HW"] * plan.shape(sn)[3] for sn in a["srcs"] if sn in self._lo_buf)
+                out.append(("gn_apply", 0, 2 * n * ab + wide))       # one read + one write (+ the int8 extensions)
             elif op.kind == "conv":
                 k = sum(plan.shape(s)[3] * taps for (s, _, taps, _) in a["segs"])
                 m = self.B * a["H"] * a["W"]
                 byts = sum(self.B * a["H"] * a["W"] * (a["stride"] ** 2 if i == 0 else 1) * plan.shape(s)[3]
                            for i, (s, _, _, _) in enumerate(a["segs"])) * ab
                 byts += k * a["cout"] * ab + m * a["cout"] * ab * (2 if a["residual"] else 1)
+                byts += m * a["cout"] if a.get("dst") in self._lo_buf else 0
                 name = "conv_sm100" if self._conv_sm100_ok(a) else "conv_simt"
                 out.append((name, 2 * m * k * a["cout"], byts))
             elif op.kind == "attn":

@@ -41,7 +41,7 @@ class UNetSpec:
 class Buf:
     name: str
     shape: Tuple[int, ...]      # logical shape (NHWC for activations)
-    kind: str                   # "act" (engine dtype) | "f32"
+    kind: str                   # "act" (engine dtype) | "f32" | "u8"
     elems: int = 0
     first: int = -1             # first op index that touches it
     last: int = -1              # last op index that touches it
@@ -104,7 +104,7 @@ class Plan:
         by_first: Dict[int, List[Buf]] = {}
         by_last: Dict[int, List[Buf]] = {}
         for b in self.bufs.values():
-            b.nbytes = b.elems * (act_bytes if b.kind == "act" else 4)
+            b.nbytes = b.elems * {"act": act_bytes, "f32": 4, "u8": 1}[b.kind]
             b.nbytes = (b.nbytes + align - 1) // align * align
             by_first.setdefault(b.first, []).append(b)
             by_last.setdefault(b.last, []).append(b)

@@ -63,9 +63,10 @@ def composite(img, shadow_mask, feature_mask, intensity, adv=None, want_shadowed
     return shadowed, out
 
 
-def composite_generated(img, x_final, centers, radii, feature_mask):
+def composite_generated(img, x_final, centers, radii, feature_mask, blur=False):
     """Fused tail of the shadow sampler: out = clamp(img*(1-m) + clip(x_final,0,1)*m, 0, 1) with
-    m = disk(centers, radii) * feature_mask built in-kernel."""
+    m = disk(centers, radii) * feature_mask built in-kernel (dm2:634-653); blur=True passes the disk through the
+    5x5 Gaussian first (tools/train_shadow.py:244-247, ddim2/test.py:851-854)."""
     _need_cuda(img, x_final, centers, radii, feature_mask)
     img = img.float().contiguous()
     xf = x_final.float().contiguous()
@@ -75,6 +76,6 @@ def composite_generated(img, x_final, centers, radii, feature_mask):
     B, Cc, H, W = img.shape
     out = torch.empty_like(img)
     with torch.cuda.device(img.device):
-        capi.call("advs_shadow_composite_generated", _p(img), _p(xf), _p(centers), _p(radii), _p(fm), fm.shape[1],
-                  _p(out), B, Cc, H, W, _st())
+        capi.call("advs_shadow_composite_generated_ex", _p(img), _p(xf), _p(centers), _p(radii), _p(fm), fm.shape[1],
+                  1 if blur else 0, _p(out), B, Cc, H, W, _st())
     return out

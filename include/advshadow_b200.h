@@ -108,6 +108,10 @@ int advs_groupnorm_finalize_ex(const float* part0, int c0, int parts0, int gran0
                                float* scale_shift, void* stream);
 int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, int HW,
                          const float* scale_shift, int silu, void* y, int dtype, void* stream);
+/* bf16 only: same, where lo0 / lo1 (each may be NULL) are the int8 mantissa extensions written by a conv epilogue
+ * through advs_conv_params.y_lo for x0 / x1. */
+int advs_groupnorm_apply_wide(const void* x0, const void* lo0, int c0, const void* x1, const void* lo1, int c1, int B,
+                              int HW, const float* scale_shift, int silu, void* y, void* stream);
 
 /* ---- K1/K2/K3: convolution as implicit GEMM (dm1:73, 86, 90, 114-115, 134, 148) ----------- */
 /* D[pixel, cout] = sum over K-segments s, taps, channels of  X_s[pixel + tap, c] * W_s[cout, tap, c]
@@ -161,6 +165,12 @@ typedef struct advs_conv_params {
    * a third of the epilogue's shuffles; usable whenever every GroupNorm reading the tensor has a multiple of 4
    * channels per group (pass the same value as gran to advs_groupnorm_finalize_ex). */
   int32_t stats_gran;
+  /* optional (out_mode 0, ADVS_BF16): "wide" storage for a tensor that a GroupNorm will read.  y stays the
+   * round-to-nearest bf16 tensor (GEMM operand / residual for every other consumer); y_lo[B,H,W,Cout] int8 holds
+   * the next 8 mantissa bits: value ~= as_float((bits(y) << 16) + ((int)y_lo << 8)), exact to 2^-17 relative.
+   * advs_groupnorm_apply_wide reads the pair, so the normalised GEMM operand is rounded once instead of twice
+   * (the reference normalises fp32 tensors, dm1:71-72, 83-84). */
+  void* y_lo;
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */
@@ -236,6 +246,19 @@ int advs_shadow_composite(const float* img, const float* shadow_mask, const floa
 int advs_shadow_composite_generated(const float* img, const float* x_final, const float* centers,
                                     const float* radii, const float* feature_mask, int Cm,
                                     float* out, int B, int C, int H, int W, void* stream);
+/* same with the mask flavour selectable: blur = 1 applies the 5x5 Gaussian to the disk mask in-kernel before the
+ * feature mask multiplies it (tools/train_shadow.py:244-247, ddim2/test.py:851-854); blur = 0 is dm2:634-642. */
+int advs_shadow_composite_generated_ex(const float* img, const float* x_final, const float* centers,
+                                       const float* radii, const float* feature_mask, int Cm, int blur,
+                                       float* out, int B, int C, int H, int W, void* stream);
+/* The sampler's fused tail: the LAST DDIM update (advs_ddim_step with noise = NULL; x_out may alias x) and the
+ * generated-shadow composite above in one pass over the images -- the north star's "update + compositing become
+ * one fused elementwise kernel".  Reference: dm1:457-472 followed by dm2:634-653 (blur = 0) or ts:244-265
+ * (blur = 1).  Bit-identical to running the two entry points one after the other. */
+int advs_ddim_step_composite(const float* x, const float* eps, float* x_out, const float* coef, int32_t* step_dev,
+                             int advance, int clip_denoised, const float* img, const float* centers,
+                             const float* radii, const float* feature_mask, int Cm, int blur, float* out, int B,
+                             int C, int H, int W, void* stream);
 
 /* ---- IDDM class-conditional UNet + CFG DDIM (model/networks/unet.py:17-128, model/modules/*.py,
  *      model/samples/ddim.py:48-100): the bandwidth ops not shared with the diff_model path ------------------ */

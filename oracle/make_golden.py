@@ -230,6 +230,143 @@ def iddm_cases():
     return out
 
 
+def dm2_256():
+    """BASELINE.json configs[1] at its own shape: dm2.UNetModel() at 256x256 (attention T=4096/dh=128 and
+    T=1024/dh=256, 128-channel full-resolution convs), B=1.  One stand-alone forward plus the teacher-forced trace
+    of steps 0, 1 and 49 of the reference's 50-step DDIM loop (dm1:416-474 with dm2's linear schedule, R1 in
+    SURVEY.md).  x_T is reproducible from its seed and is not stored."""
+    dm1, dm2 = R.dm1(), R.dm2()
+    torch.manual_seed(0)
+    model = dm2.UNetModel().eval()
+    out = {"dm2_checksum": weight_checksum(model)}
+    g = torch.Generator().manual_seed(256)
+    x = torch.randn(1, 3, 256, 256, generator=g)
+    t = torch.tensor([741])
+    with torch.no_grad():
+        out["fwd"] = dict(x=x, t=t, eps=model(x, t))
+    gd = dm1.GaussianDiffusion(timesteps=1000, beta_schedule="linear")
+    torch.manual_seed(1234)
+    x_T = torch.randn(1, 3, 256, 256)
+    trace = []
+
+    class Wrap(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x, t):
+            e = self.m(x, t)
+            trace.append((x.clone(), t.clone(), e.clone()))
+            return e
+
+    saved = dm1.torch
+    dm1.torch = patched_randn(dm1, [x_T])
+    try:
+        final = gd.ddim_sample(Wrap(model), 256, batch_size=1, channels=3, ddim_timesteps=50)
+    finally:
+        dm1.torch = saved
+    assert len(trace) == 50 and torch.equal(trace[0][0], x_T)
+    keep = (0, 1, 49)
+    out["ddim"] = dict(x_T_seed=1234, steps=keep, n=50,
+                       x=[None if i == 0 else trace[i][0] for i in keep],          # step 0's input is x_T
+                       t=torch.stack([trace[i][1] for i in keep]),
+                       eps=torch.stack([trace[i][2] for i in keep]),
+                       x_next=[trace[2][0], torch.from_numpy(final)])              # after step 1, after step 49
+    return out
+
+
+def _ts_functions():
+    """The blur-flavour compositing functions of tools/train_shadow.py (ts:147-174, 224-266), taken from the
+    reference SOURCE TEXT and executed unmodified: the module itself cannot be imported (fastai, config.choices)."""
+    import ast
+    import cv2
+    import torch.nn.functional as F
+    path = os.path.join(R.REF_ROOT, "tools", "train_shadow.py")
+    src = open(path, encoding="utf-8").read()
+    ns = {"torch": torch, "cv2": cv2, "F": F, "np": np}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("apply_gaussian_blur", "create_shadow_mask", "apply_shadow"):
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return ns
+
+
+def shadow_blur_cases():
+    """apply_shadow with the 5x5 Gaussian-blurred mask: ts flavour (intensity 0.43, ts:224-266) and the
+    ddim2/test.py flavour (same arithmetic, intensity 0.051, dt:830-871), adversarial image injected."""
+    ns = _ts_functions()
+    cases = []
+    g = torch.Generator().manual_seed(13)
+    for (H, W, Cm, cx, cy, r, inten, soft) in [(64, 64, 1, 31.5, 30.25, 20.0, 0.43, False), (128, 96, 3, 40.0, 70.5, 25.0, 0.43, True),
+                                               (120, 160, 1, 100.3, 60.7, 45.5, 0.051, False), (32, 32, 1, 2.0, 1.0, 12.0, 0.051, True)]:
+        img = torch.rand(3, H, W, generator=g)
+        fm = torch.rand(Cm, H, W, generator=g)
+        if not soft:
+            fm = (fm > 0.4).float()
+        adv = torch.rand(3, H, W, generator=g)
+        seen = {}
+
+        def perturb(classifier, shadowed, label, device, mask, epsilon, adv=adv, seen=seen):
+            seen["shadowed"], seen["mask"] = shadowed.clone(), mask.clone()
+            return adv
+
+        ns["apply_adversarial_perturbation"] = perturb
+        c, rr = torch.tensor([cx, cy]), torch.tensor(r)
+        out = ns["apply_shadow"](img, c, rr, fm, None, None, "cpu", shadow_intensity=inten)
+        cases.append(dict(img=img, fm=fm, adv=adv, center=c, radius=rr, intensity=inten,
+                          blurred=ns["apply_gaussian_blur"](ns["create_shadow_mask"]((3, H, W), c, rr, "cpu")),
+                          combined=seen["mask"], shadowed=seen["shadowed"], out=out))
+    return cases
+
+
+class _TinyVictim(torch.nn.Module):
+    """Seeded stand-in for the fastai learner's `.model` (the victim stays PyTorch on both sides)."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, stride=2, padding=1), torch.nn.Tanh(),
+                                       torch.nn.Conv2d(8, 8, 3, stride=2, padding=1), torch.nn.Tanh(),
+                                       torch.nn.AdaptiveAvgPool2d(4), torch.nn.Flatten(), torch.nn.Linear(128, 37))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def shadow_opt_cases():
+    """The reference's own optimize_shadow_position (dm2:457-550, with apply_shadow dm2:615-654 and the FGSM
+    step dm2:572-613) run for 10 iterations against a tiny seeded victim, per image."""
+    dm2 = R.dm2()
+
+    class _NoPlot:      # the reference plots at iteration 0 (dm2:510-536); matplotlib is a stub here
+        def __getattr__(self, k):
+            return lambda *a, **kw: (_NoPlot(), [_NoPlot()] * 8) if k == "subplots" else _NoPlot()
+
+        def __call__(self, *a, **kw):
+            return _NoPlot()
+
+    dm2.plt = _NoPlot()
+    torch.manual_seed(77)
+    victim = _TinyVictim().eval()
+
+    class Classifier:
+        model = victim
+
+    gd = dm2.GaussianDiffusion()
+    g = torch.Generator().manual_seed(8)
+    S = 32
+    yy, xx = torch.meshgrid(torch.arange(S), torch.arange(S), indexing="ij")
+    cases = []
+    for (cx, cy, lab) in ((10, 12, 3), (20, 16, 7), (15, 22, 11)):
+        img = torch.rand(3, S, S, generator=g)
+        mask = (((xx - cx) ** 2 + (yy - cy) ** 2) <= 100).float()[None]
+        label = torch.tensor([lab])
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            c, r, out = gd.optimize_shadow_position(Classifier, img.clone(), mask.clone(), label, "cpu", iterations=10)
+        cases.append(dict(img=img, mask=mask, label=label, center=c, radius=r, out=out.detach()))
+    return dict(cases=cases, victim_state={k: v.clone() for k, v in victim.state_dict().items()}, iterations=10)
+
+
 def schedules():
     dm1, dm2 = R.dm1(), R.dm2()
     out = {}
@@ -238,14 +375,13 @@ def schedules():
     return out
 
 
+MINTERS = dict(config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+               iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    torch.save(config1(), os.path.join(OUT, "config1.pt"))
-    torch.save(forwards(), os.path.join(OUT, "forwards.pt"))
-    torch.save(shadow_cases(), os.path.join(OUT, "shadow.pt"))
-    torch.save(schedules(), os.path.join(OUT, "schedules.pt"))
-    torch.save(stochastic_cases(), os.path.join(OUT, "stochastic.pt"))
-    torch.save(iddm_cases(), os.path.join(OUT, "iddm.pt"))
+    for name in (sys.argv[1:] or list(MINTERS)):      # `python oracle/make_golden.py [name ...]`
+        torch.save(MINTERS[name](), os.path.join(OUT, name + ".pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -161,3 +161,50 @@ def apply_shadow(img, center, radius, fmask, intensity=0.33, perturb=None, blur=
     shadowed = img * (1 - m) + m * (img * (1 - intensity))
     adv = perturb(shadowed) if perturb is not None else shadowed[None]
     return torch.clamp(img * (1 - m) + adv * m, 0, 1), shadowed, m
+
+
+def fgsm_perturb(victim, image, target_label, epsilon):                  # ddim2/diff_model2.py:572-613
+    x = image.detach().clone()[None].requires_grad_(True)
+    with torch.enable_grad():
+        loss = F.cross_entropy(victim(x), target_label)
+        victim.zero_grad()
+        loss.backward()
+    return torch.clamp(x + epsilon * x.grad.data.sign(), 0, 1).detach()
+
+
+def optimize_shadow_position(victim, img, mask, target_label, lr=1e-1, iterations=10, intensity=0.33, epsilon=0.01):
+    """ddim2/diff_model2.py:457-550: Adam on (centre, radius); the hard disk mask passes no gradient, so only the
+    regulariser moves them.  Returns (centre, radius, last shadowed image [1,C,H,W])."""
+    mask_center = torch.nonzero(mask).float().mean(0)[1:]
+    center = torch.nn.Parameter(mask_center.clone(), requires_grad=True)
+    radius = torch.nn.Parameter(torch.tensor(20.0), requires_grad=True)
+    opt = torch.optim.Adam([center, radius], lr=lr)
+    out = None
+    for _ in range(iterations):
+        opt.zero_grad()
+        out, _, _ = apply_shadow(img, center, radius, mask, intensity,
+                                 perturb=lambda s: fgsm_perturb(victim, s, target_label, epsilon))
+        x = out.squeeze(0) if out.dim() == 4 else out
+        adv = -F.cross_entropy(victim(x.unsqueeze(0)), target_label)
+        nat = F.mse_loss(x, img)
+        reg = (center - mask_center).pow(2).sum() + radius.pow(2)
+        (adv + nat + 0.1 * reg).backward()
+        if center.grad is not None and radius.grad is not None:
+            opt.step()
+        with torch.no_grad():
+            center.clamp_(min=0, max=img.size(2))
+            radius.clamp_(min=0, max=min(img.size(1), img.size(2)) / 2)
+    return center.detach(), radius.detach(), out
+
+
+class TinyVictim(torch.nn.Module):
+    """The seeded stand-in victim of tests/golden/shadow_opt.pt (same layers as oracle/make_golden._TinyVictim)."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, stride=2, padding=1), torch.nn.Tanh(),
+                                       torch.nn.Conv2d(8, 8, 3, stride=2, padding=1), torch.nn.Tanh(),
+                                       torch.nn.AdaptiveAvgPool2d(4), torch.nn.Flatten(), torch.nn.Linear(128, 37))
+
+    def forward(self, x):
+        return self.net(x)

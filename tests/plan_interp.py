@@ -31,8 +31,17 @@ def temb_table(plan, params, timesteps):
     return torch.cat(cols, 1)
 
 
-def run_plan(plan, params, x, timesteps, round_bf16=False):
+def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2):
+    """`wide_prenorm` (with round_bf16): conv outputs of that many top-resolution levels keep an unrounded copy that
+    only GroupNorm reads (the engine's bf16 + int8 mantissa-extension storage, exact to 2^-17)."""
     rnd = (lambda t: t.to(torch.bfloat16).float()) if round_bf16 else (lambda t: t)
+    wide = {}
+
+    def store(dst, t_nhwc):
+        bufs[dst] = rnd(t_nhwc)
+        if round_bf16 and (t_nhwc.shape[1] << wide_prenorm) > plan.H and t_nhwc.shape[3] % 32 == 0:
+            wide[dst] = t_nhwc
+
     wr = (lambda t: t.to(torch.bfloat16).float()) if round_bf16 else (lambda t: t)   # weight rounding
     table = temb_table(plan, params, timesteps)
     if table.shape[0] == 1:
@@ -43,9 +52,9 @@ def run_plan(plan, params, x, timesteps, round_bf16=False):
         a = op.args
         if op.kind == "stem":
             y = F.conv2d(x, params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
-            bufs[a["dst"]] = rnd(_nhwc(y))
+            store(a["dst"], _nhwc(y))
         elif op.kind == "gn":
-            xin = torch.cat([bufs[s] for s in a["srcs"]], 3)
+            xin = torch.cat([wide.get(s, bufs[s]) for s in a["srcs"]], 3)
             y = F.group_norm(_nchw(xin), a["groups"], params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], 1e-5)
             if a["silu"]:
                 y = F.silu(y)
@@ -78,7 +87,7 @@ def run_plan(plan, params, x, timesteps, round_bf16=False):
                 bufs[a["qkv"][1]] = rnd((qkv[:, :, 1] * scale).transpose(2, 3).contiguous())
                 bufs[a["qkv"][2]] = rnd(qkv[:, :, 2].contiguous())                              # [B,h,dh,T]
             else:
-                bufs[a["dst"]] = rnd(_nhwc(acc))
+                store(a["dst"], _nhwc(acc))
         elif op.kind == "attn":
             q, k, vt = bufs[a["q"]], bufs[a["k"]], bufs[a["vt"]]
             s = torch.einsum("bhtd,bhsd->bhts", q, k).softmax(-1)
@@ -92,7 +101,7 @@ def run_plan(plan, params, x, timesteps, round_bf16=False):
         elif op.kind == "upconv":
             y = F.interpolate(_nchw(bufs[a["src"]]), scale_factor=2, mode="nearest")
             y = F.conv2d(y, wr(params[a["weight"] + ".weight"]), params[a["weight"] + ".bias"], padding=1)
-            bufs[a["dst"]] = rnd(_nhwc(y))
+            store(a["dst"], _nhwc(y))
         elif op.kind == "head":
             eps = F.conv2d(_nchw(bufs[a["src"]]), params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
         else:

@@ -54,9 +54,19 @@ def _worker(rank, world, port, n_items, q):
     labels[::3] = logits[::3].argmax(1)
     lo, hi = shard_bounds(n_items, world, rank)
     flags = (logits[lo:hi].argmax(1) != labels[lo:hi]).to(torch.uint8)       # decision rule, ASR_fast.py:117-121
-    allf, counts = exchange_success(flags)
+    pad_to = -(-n_items // world)                      # the widest shard
+    allf, counts = exchange_success(flags, pad_to=pad_to)
     ref = (logits.argmax(1) != labels).to(torch.uint8)
     ok = bool(torch.equal(allf, ref)) and counts.tolist() == [int(ref.sum()), n_items]
+    # counts handed over from the device kernel (here: computed on the host) are used as they are
+    mine = torch.tensor([int(flags.sum()), flags.numel()], dtype=torch.int64)
+    allf2, counts2 = exchange_success(flags, pad_to=pad_to, counts_local=mine)
+    ok = ok and bool(torch.equal(allf2, ref)) and counts2.tolist() == counts.tolist() and mine.tolist() == [int(flags.sum()), flags.numel()]
+    try:
+        exchange_success(flags)                        # no size handshake: the width must be given
+        ok = False
+    except ValueError:
+        pass
     q.put((rank, ok))
     dist.barrier()
     dist.destroy_process_group()

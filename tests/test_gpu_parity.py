@@ -50,6 +50,7 @@ FORWARD_CASES = [("dm1", "dm1_32", "dm1_checksum"), ("dm1", "dm1_64", "dm1_check
                          [("fp32", "simt", "simt", True, TOL_FP32), ("bf16", "simt", "simt", True, TOL_BF16),
                           ("bf16", "sm100", "simt", True, TOL_BF16), ("bf16", "sm100", "sm100", False, TOL_BF16),
                           ("bf16", "sm100", "sm100", "no_upfuse", TOL_BF16),
+                          ("bf16", "sm100", "sm100", "narrow", TOL_BF16),
                           ("bf16", "sm100", "sm100", True, TOL_BF16)])
 def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision, conv, attn, fuse, tol):
     g = golden("forwards.pt")
@@ -59,7 +60,8 @@ def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision
     assert abs(chk - want) <= 1e-6 * want, "seeded weights differ from the fixture"
     x, t = case["x"].cuda(), case["t"].cuda()
     eng = model.engine(x.shape[0], x.shape[2], x.shape[3], precision=precision, conv_impl=conv, attn_impl=attn,
-                       fuse_gn_stats=bool(fuse), fuse_upsample=(fuse != "no_upfuse"))
+                       fuse_gn_stats=bool(fuse), fuse_upsample=(fuse != "no_upfuse"),
+                       wide_prenorm=(0 if fuse == "narrow" else 2))
     eps = eng.forward(x, t)
     torch.cuda.synchronize()
     err = (eps.cpu() - case["eps"]).abs().max().item()
@@ -118,9 +120,7 @@ def test_config1_teacher_forced_steps(pkg, golden, precision, tol):
         assert torch.equal(out.cpu(), want_next), f"DDIM update differs from the reference at step {i}"
     errs.sort()
     print(f"teacher-forced {precision}: max|eps err| per step: median {errs[n // 2]:.3e}, worst {worst:.3e}")
-    # bf16: max-abs over 12 288 outputs of a ~4e-3-sigma rounding error fluctuates step to step
-    # (DESIGN.md "bf16 error budget"); the median step must meet the tolerance, no step may exceed 1.5x
-    assert errs[n // 2] <= tol and worst <= (tol if precision == "fp32" else 1.5 * tol)
+    assert worst <= tol                     # every step, both modes (BASELINE.json: 1e-4 fp32, 2e-2 bf16)
     model.release_engines()
 
 
@@ -355,8 +355,13 @@ def test_shadow_sampler_multi_stream_matches_single_stream(pkg):
             torch.full((B, 2), S / 2.0), torch.tensor([5.0, 8.0, 11.0, 14.0]))
     one = ShadowSampler(model, gd, B, S, ddim_timesteps=n)(*args).clone()
     two = ShadowSampler(model, gd, B, S, ddim_timesteps=n, streams=2)(*args).clone()
-    assert (one - two).abs().max().item() < 5e-2      # bf16 runs with different reduction tiling; same images
-    assert (one - two).abs().mean().item() < 2e-3
+    # No reduction in the path depends on the batch size (GroupNorm partial sums are chunked per image size only,
+    # conv / attention tiles never mix images in a sum), so a trajectory is bit-reproducible in any (sub-)batch.
+    # (Round 1 chunked the statistics by batch size: fp32 summation-order noise, amplified by 1/sqrt(a_t) over the
+    # steps, showed up as a 5e-2 difference here.)
+    assert torch.equal(one, two)
+    solo = ShadowSampler(model, gd, 1, S, ddim_timesteps=n)(*(a[2:3] for a in args)).clone()
+    assert torch.equal(solo[0], one[2])
     model.release_engines()
 
 
@@ -430,3 +435,183 @@ def test_batched_shadow_optimisation_equals_per_image_loop(pkg):
         assert torch.allclose(cb[i].cpu(), c.cpu(), atol=1e-5) and abs(float(rb[i]) - float(r)) < 1e-5
         assert torch.allclose(ob[i], o[0], atol=1e-6)
     assert float(rb.max()) < 20.0        # Adam on the regulariser shrank the radii, as in the reference
+
+
+def test_dm2_at_256_forward_and_teacher_forced_steps(pkg, golden):
+    """The headline shape itself (BASELINE.json configs[1]: dm2.UNetModel() at 256x256): attention at T=4096/dh=128
+    and T=1024/dh=256, the 128-channel full-resolution halo convs at W=256, halo<256> at W=128.  One forward and
+    steps 0, 1, 49 of the reference's DDIM-50 loop (linear schedule), teacher-forced; fp32 <= 1e-4, bf16 <= 2e-2."""
+    from advshadow_b200 import _capi as capi
+    import ctypes as C
+    g = golden("dm2_256.pt")
+    model, chk = get_model(pkg, "dm2")
+    assert abs(chk - g["dm2_checksum"]) <= 1e-6 * chk
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000, beta_schedule="linear")
+    d = g["ddim"]
+    torch.manual_seed(d["x_T_seed"])
+    x_T = torch.randn(1, 3, 256, 256)
+    seq, prev = pkg["dm1"].ddim_timestep_tables(1000, d["n"], "uniform")
+    coef = gd.ddim_coefficients(seq, prev, d["n"], 0.0).cuda()
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for precision, tol in (("bf16", TOL_BF16), ("fp32", TOL_FP32)):
+        eng = model.engine(1, 256, 256, precision=precision)
+        if precision == "bf16":
+            names = [n for (_, _, n) in eng._launches]
+            assert "attn_sm100" in names and "conv_sm100" in names and "attn_simt" not in names and "conv_simt" not in names
+        e = eng.forward(g["fwd"]["x"].cuda(), g["fwd"]["t"].cuda())
+        err = (e.cpu() - g["fwd"]["eps"]).abs().max().item()
+        print(f"dm2 256x256 {precision}: forward max|eps err| = {err:.3e} (|eps|max {g['fwd']['eps'].abs().max():.2f})")
+        assert err <= tol
+        for j, i in enumerate(d["steps"]):
+            x = (x_T if d["x"][j] is None else d["x"][j]).cuda()
+            e = eng.forward(x, d["t"][j].cuda())
+            err = (e.cpu() - d["eps"][j]).abs().max().item()
+            print(f"dm2 256x256 {precision}: DDIM-50 step {i} (t={int(d['t'][j])}) max|eps err| = {err:.3e}")
+            assert err <= tol
+            if j >= 1:      # the update applied to the oracle's eps reproduces the oracle's next state bit for bit
+                out = torch.empty_like(x)
+                step.fill_(i)
+                capi.call("advs_ddim_step", x.data_ptr(), d["eps"][j].cuda().data_ptr(), None, out.data_ptr(), x.numel(),
+                          coef.data_ptr(), step.data_ptr(), 0, 1, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                assert torch.equal(out.cpu(), d["x_next"][j - 1])
+        model.release_engines()
+
+
+def test_blur_flavour_composites_bit_exact(pkg, golden):
+    """apply_shadow with the 5x5-blurred mask (tools/train_shadow.py:224-266, I=0.43; ddim2/test.py:830-871, I=0.051)
+    against the reference's own function bodies (tests/golden/shadow_blur.pt)."""
+    sh = pkg["shadow"]
+    for c in golden("shadow_blur.pt"):
+        img, fm, adv = c["img"].cuda(), c["fm"].cuda(), c["adv"].cuda()
+        H, W = img.shape[1:]
+        cen, rad = c["center"][None].cuda(), c["radius"][None].cuda()
+        mb = sh.gaussian_blur5(sh.disk_mask(cen, rad, H, W))
+        assert torch.equal(mb[0].cpu(), c["blurred"])
+        shadowed, out = sh.composite(img[None], mb, fm[None], c["intensity"], adv=adv[None])
+        assert torch.equal(shadowed[0].cpu(), c["shadowed"]) and torch.equal(out[0].cpu(), c["out"])
+        # the sampler's fused tail: mask + blur built in-kernel, the generated image (already in [0,1]) injected
+        fused = sh.composite_generated(img[None], adv[None], cen, rad, fm[None], blur=True)
+        assert torch.equal(fused[0].cpu(), c["out"])
+
+
+@pytest.mark.parametrize("flavour,blur", [("dm2", False), ("ts", True), ("dt", True)])
+def test_shadow_sampler_tail_flavours_equal_oracle_chain(pkg, flavour, blur):
+    """ShadowSampler's fused last-step kernel == oracle port: apply_shadow(blur) on the sampler's own final x_0."""
+    from oracle import torch_port as P
+    from advshadow_b200.sampler import ShadowSampler
+    model, _ = get_model(pkg, "dm1")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    B, S, n = 3, 32, 3
+    g = torch.Generator().manual_seed(5)
+    x_T, clean = torch.randn(B, 3, S, S, generator=g), torch.rand(B, 3, S, S, generator=g)
+    fmask = (torch.rand(B, 1, S, S, generator=g) > 0.2).float()
+    centers = torch.tensor([[16.0, 14.5], [1.0, 30.0], [25.2, 8.1]])
+    radii = torch.tensor([9.0, 12.5, 6.0])
+    smp = ShadowSampler(model, gd, B, S, ddim_timesteps=n, shadow_flavour=flavour)
+    out = smp(x_T, clean, fmask, centers, radii)
+    x0 = smp.eng.x.cpu()
+    for i in range(B):
+        ref = P.apply_shadow(clean[i], centers[i], radii[i], fmask[i], 0.43 if flavour == "ts" else 0.33,
+                             perturb=lambda s_, i=i: x0[i].clamp(0, 1)[None], blur=blur)[0][0]
+        assert torch.equal(out[i], ref), (flavour, i)
+    model.release_engines()
+
+
+def test_whole_trajectory_graph_equals_per_step_graphs_and_eager(pkg):
+    """One CUDA graph for the whole trajectory (n steps + fused composite) == n replays of a one-step graph == eager."""
+    from advshadow_b200.sampler import ShadowSampler
+    model, _ = get_model(pkg, "dm1")
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    B, S, n = 2, 32, 5
+    g = torch.Generator().manual_seed(6)
+    args = (torch.randn(B, 3, S, S, generator=g), torch.rand(B, 3, S, S, generator=g), torch.ones(B, 1, S, S),
+            torch.full((B, 2), S / 2.0), torch.tensor([7.0, 12.0]))
+    outs = [ShadowSampler(model, gd, B, S, ddim_timesteps=n, graph_scope=scope, use_graph=use)(*args).clone()
+            for scope, use in (("trajectory", True), ("step", True), ("trajectory", False))]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    smp = ShadowSampler(model, gd, B, S, ddim_timesteps=n)
+    a = smp(*args).clone()
+    b = smp(*args).clone()            # the graph resets its own step counter: replays are idempotent
+    assert torch.equal(a, b) and torch.equal(a, outs[0])
+    model.release_engines()
+
+
+def test_sampler_follows_weight_updates(pkg):
+    """weights changed after the sampler (and its CUDA graph) was built -- load_state_dict, in-place edits,
+    re-assigned parameter storage -- must be picked up by the next batch; captured graphs stay valid because the
+    engine owns every buffer the kernels read."""
+    from advshadow_b200.sampler import ShadowSampler
+    torch.manual_seed(0)
+    model = pkg["dm1"].UNetModel(model_channels=64, channel_mult=(1, 2), attention_resolutions=(2,), num_res_blocks=1).eval().cuda()
+    gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
+    B, S, n = 2, 32, 3
+    g = torch.Generator().manual_seed(7)
+    args = (torch.randn(B, 3, S, S, generator=g), torch.rand(B, 3, S, S, generator=g), torch.ones(B, 1, S, S),
+            torch.full((B, 2), S / 2.0), torch.tensor([9.0, 13.0]))
+    smp = ShadowSampler(model, gd, B, S, ddim_timesteps=n)
+    before = smp(*args).clone()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    torch.manual_seed(123)
+    new_sd = {k: (v + 0.05 * torch.randn_like(v)) for k, v in sd.items()}
+    model.load_state_dict(new_sd)                                   # in-place copy into the same storage
+    after = smp(*args).clone()
+    fresh = ShadowSampler(model, gd, B, S, ddim_timesteps=n, use_graph=False)(*args).clone()
+    assert not torch.equal(before, after) and torch.equal(after, fresh)
+    model.load_state_dict(sd, assign=True)                          # parameter storage replaced
+    again = smp(*args).clone()
+    assert torch.equal(again, before)
+    with torch.no_grad():
+        getattr(model.out, "0").weight.mul_(1.5)                               # GroupNorm affine edited in place
+    edited = smp(*args).clone()
+    fresh = ShadowSampler(model, gd, B, S, ddim_timesteps=n, use_graph=False)(*args).clone()
+    assert torch.equal(edited, fresh) and not torch.equal(edited, before)
+    model.release_engines()
+
+
+def test_two_devices_in_one_process(pkg, golden):
+    """kernel attributes (dynamic shared memory) are per device; a second GPU in the same process must work."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = golden("forwards.pt")["dm1_32"]
+    outs = []
+    for dev in (0, 1):
+        torch.manual_seed(0)
+        m = pkg["dm1"].UNetModel().eval().to(f"cuda:{dev}")
+        with torch.cuda.device(dev):
+            outs.append(m(g["x"].to(f"cuda:{dev}"), g["t"].to(f"cuda:{dev}")).cpu())
+    assert torch.equal(outs[0], outs[1]) and (outs[0] - g["eps"]).abs().max().item() <= TOL_BF16
+
+
+def test_shadow_optimisation_matches_reference_golden(pkg, golden):
+    """SURVEY 8f row 3 against the REFERENCE: optimize_shadow_position (dm2:457-550, with apply_shadow dm2:615-654 and
+    the FGSM step dm2:572-613), 10 iterations, tiny seeded victim -- single-image and batched methods vs the centre /
+    radius / final image the reference's own code produced (tests/golden/shadow_opt.pt).  The victim runs in PyTorch
+    on the GPU here and on the CPU in the golden: FGSM takes the SIGN of its gradient, so an element whose gradient is
+    within float noise of zero may flip and move that pixel by 2*epsilon."""
+    from oracle import torch_port as P
+    g = golden("shadow_opt.pt")
+    gd = pkg["dm2"].GaussianDiffusion()
+
+    class Victim:
+        model = P.TinyVictim().eval()
+
+    Victim.model.load_state_dict(g["victim_state"])
+    Victim.model.cuda()
+    imgs = torch.stack([c["img"] for c in g["cases"]]).cuda()
+    masks = torch.stack([c["mask"] for c in g["cases"]]).cuda()
+    labels = torch.cat([c["label"] for c in g["cases"]]).cuda()
+
+    def check(center, radius, out, c, who):
+        assert torch.allclose(center.cpu(), c["center"], atol=1e-5), who
+        assert abs(float(radius) - float(c["radius"])) < 1e-5, who
+        diff = (out.cpu().reshape(c["out"].shape) - c["out"]).abs()
+        flipped = (diff > 1e-6).float().mean().item()
+        print(f"{who}: centre {center.tolist()}, radius {float(radius):.4f}; {flipped:.5f} of the pixels differ, max {diff.max():.4f}")
+        assert flipped <= 2e-3 and diff.max().item() <= 0.0201
+
+    for i, c in enumerate(g["cases"]):
+        ctr, rad, out = gd.optimize_shadow_position(Victim, imgs[i], masks[i], labels[i:i + 1], "cuda", iterations=g["iterations"])
+        check(ctr, rad, out, c, f"single image {i}")
+    cb, rb, ob = gd.optimize_shadow_position_batched(Victim, imgs, masks, labels, "cuda", iterations=g["iterations"])
+    for i, c in enumerate(g["cases"]):
+        check(cb[i], rb[i], ob[i], c, f"batched image {i}")

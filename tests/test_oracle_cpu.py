@@ -60,6 +60,33 @@ def test_port_dm2_forward_matches_reference_golden(golden):
     assert (e - c["eps"]).abs().max().item() < 2e-5
 
 
+def test_port_dm2_at_256_matches_reference_golden(golden):
+    """The headline shape (configs[1]: dm2.UNetModel() at 256x256): the port's forward and its DDIM updates against
+    the reference's own 50-step run (tests/golden/dm2_256.pt)."""
+    g = golden("dm2_256.pt")
+    m, p = seeded_params("dm2")
+    chk = float(sum(v.detach().double().abs().sum() for v in m.parameters()))
+    assert abs(chk - g["dm2_checksum"]) <= 1e-9 * chk
+    with torch.no_grad():
+        e = P.unet_forward(p, P.DM2_CFG, g["fwd"]["x"], g["fwd"]["t"])
+    assert (e - g["fwd"]["eps"]).abs().max().item() < 2e-5
+    d = g["ddim"]
+    acp = P.linear_alphas_cumprod()
+    seq = np.asarray(list(range(0, 1000, 1000 // d["n"]))) + 1
+    prev = np.append(np.array([0]), seq[:-1])
+    torch.manual_seed(d["x_T_seed"])
+    x_T = torch.randn(1, 3, 256, 256)
+    assert [int(t) for t in d["t"].flatten()] == [int(seq[d["n"] - 1 - i]) for i in d["steps"]]
+    for j, i in enumerate(d["steps"]):
+        k = d["n"] - 1 - i
+        a_t = acp[int(seq[k])].float().reshape(1, 1, 1, 1)
+        a_p = acp[int(prev[k])].float().reshape(1, 1, 1, 1)
+        x = x_T if d["x"][j] is None else d["x"][j]
+        nxt = P.ddim_update(x, d["eps"][j], a_t, a_p)
+        want = d["x"][1] if j == 0 else d["x_next"][j - 1]
+        assert torch.equal(nxt, want), f"DDIM update of step {i} differs"
+
+
 def test_port_ddim_config1_matches_reference_golden(golden, dm1_params):
     g = golden("config1.pt")
     _, p = dm1_params
@@ -90,6 +117,27 @@ def test_port_shadow_matches_reference_golden(golden):
     out, shadowed, _ = P.apply_shadow(g["clean"], g["center"], g["radius"], g["feature_mask"], 0.33,
                                       perturb=lambda s: gen01)
     assert torch.equal(out, g["composite"]) and torch.equal(shadowed, g["shadowed"])
+
+
+def test_port_blur_flavour_matches_reference_golden(golden):
+    """tools/train_shadow.py:224-266 (I=0.43) and ddim2/test.py:830-871 (I=0.051): 5x5-blurred mask flavours,
+    golden = the reference's own function bodies executed by oracle/make_golden.shadow_blur_cases."""
+    for c in golden("shadow_blur.pt"):
+        H, W = c["img"].shape[1:]
+        assert torch.equal(P.gaussian_blur5(P.create_shadow_mask(H, W, c["center"], c["radius"])), c["blurred"])
+        out, shadowed, m = P.apply_shadow(c["img"], c["center"], c["radius"], c["fm"], c["intensity"],
+                                          perturb=lambda s: c["adv"], blur=True)
+        assert torch.equal(m, c["combined"]) and torch.equal(shadowed, c["shadowed"]) and torch.equal(out, c["out"])
+
+
+def test_port_shadow_optimisation_matches_reference_golden(golden):
+    """the restated optimize_shadow_position equals the reference's (dm2:457-550) on its golden."""
+    g = golden("shadow_opt.pt")
+    victim = P.TinyVictim().eval()
+    victim.load_state_dict(g["victim_state"])
+    for c in g["cases"]:
+        ctr, rad, out = P.optimize_shadow_position(victim, c["img"], c["mask"], c["label"], iterations=g["iterations"])
+        assert torch.equal(ctr, c["center"]) and torch.equal(rad, c["radius"]) and torch.equal(out, c["out"])
 
 
 def test_port_blur_matches_cv2():
@@ -173,7 +221,7 @@ def test_capi_library_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.advs_version() >= 100
     import ctypes
-    assert ctypes.sizeof(_capi.ConvParams) == 192
+    assert ctypes.sizeof(_capi.ConvParams) == 200
 
 
 def test_no_cpu_fallback_and_error_surface(dm1_params):
