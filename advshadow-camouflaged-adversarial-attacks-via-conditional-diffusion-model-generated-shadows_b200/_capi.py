@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libadvshadow_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 CONV_PLAN_BYTES = 2048
 ATTN_PLAN_BYTES = 1024
 
@@ -37,6 +37,7 @@ class ConvParams(C.Structure):
         ("stats_partial", C.c_void_p),
         ("up_phase", C.c_int32), ("stats_gran", C.c_int32),
         ("y_lo", C.c_void_p),
+        ("operand_f16", C.c_int32),
     ]
 
 
@@ -60,10 +61,12 @@ SIGNATURES = {
     "advs_groupnorm_finalize": (C.c_int, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "advs_groupnorm_finalize_ex": (C.c_int, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "advs_stem_im2col": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "advs_stem_im2col_ex": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "advs_pack_stem_weight": (C.c_int, [_vp, _vp, _i, _i, _vp]),
+    "advs_pack_stem_weight_ex": (C.c_int, [_vp, _vp, _i, _i, _i, _vp]),
     "advs_conv_sm100_stats_parts": (C.c_int, [_i, _i, _i]),
     "advs_groupnorm_apply": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
-    "advs_groupnorm_apply_wide": (C.c_int, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "advs_groupnorm_apply_wide": (C.c_int, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp]),
     "advs_conv_simt": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_plan": (C.c_int, [C.POINTER(ConvParams), _vp]),
     "advs_conv_sm100_launch": (C.c_int, [_vp, _vp]),

@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static_assert(sizeof(advs_conv_params) == 208, "advs_conv_params layout changed: update _capi.ConvParams and the tests");
 constexpr int kMaxDevices = 64;
 static std::atomic<unsigned char> g_once[kOnceSlots][kMaxDevices];
 static std::atomic<int> g_sms[kMaxDevices];
@@ -62,6 +63,7 @@ int validate_conv(const advs_conv_params* p, const char* who) {
   ADVS_CHECK_ARG(p->dtype == ADVS_F32 || p->dtype == ADVS_BF16, "%s: bad dtype", who);
   ADVS_CHECK_ARG(!p->y_lo || (p->out_mode == 0 && p->dtype == ADVS_BF16 && ((uintptr_t)p->y_lo % 32) == 0 && p->Cout % 32 == 0),
                  "%s: y_lo needs out_mode 0, bf16, Cout %% 32 == 0 and a 32-byte aligned pointer", who);
+  ADVS_CHECK_ARG(p->operand_f16 == 0 || p->dtype == ADVS_BF16, "%s: operand_f16 goes with the bf16 (16-bit) mode", who);
   if (p->out_mode == 0) {
     ADVS_CHECK_ARG(p->y != nullptr, "%s: y is null", who);
   } else if (p->out_mode == 1) {

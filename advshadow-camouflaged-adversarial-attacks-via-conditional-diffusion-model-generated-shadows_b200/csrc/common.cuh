@@ -1,6 +1,7 @@
 // Shared helpers for the advshadow_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -91,6 +92,7 @@ __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 // bf16-mode SiLU: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- one MUFU op (tanh.approx, rel. err 2^-11,
 // below bf16 resolution) instead of ex2 + rcp; GN+SiLU is MUFU-bound otherwise.
@@ -179,9 +181,14 @@ __device__ __forceinline__ uint32_t wide_encode4(const float* v, uint32_t w01, u
   return __byte_perm(__byte_perm(t0, t1, 0x0051), __byte_perm(t2, t3, 0x0051), 0x5410);
 }
 // element k (0..3) of a packed int8 word as (int)lo << 8
+// (one PRMT: result bytes = {0, byte K, sign(byte K), sign(byte K)}; the sign-replication bit of the selector
+// nibbles is a feature of the PTX instruction -- __byte_perm() only honours the low three bits of each nibble)
 template <int K>
 __device__ __forceinline__ int wide_lo_shifted(uint32_t lo4) {
-  return (int)__byte_perm(lo4, 0u, K == 0 ? 0x8804 : (K == 1 ? 0x9914 : (K == 2 ? 0xAA24 : 0xBB34)));
+  constexpr uint32_t sel = K == 0 ? 0x8804u : (K == 1 ? 0x9914u : (K == 2 ? 0xAA24u : 0xBB34u));
+  int r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo4), "r"(0u), "r"(sel));
+  return r;
 }
 // 8 bf16 (uint4) + 8 int8 (uint2) -> 8 floats
 __device__ __forceinline__ void wide_decode8(const uint4& hi, const uint2& lo, float* f) {

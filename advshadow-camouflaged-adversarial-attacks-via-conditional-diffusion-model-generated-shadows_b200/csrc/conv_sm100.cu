@@ -108,7 +108,9 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp walks the schedule, one elected lane issues) =================
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      const uint32_t idesc0 = umma_idesc_f16kind(128, BN, (a.operand_f16 & 1) != 0, (a.operand_f16 & 4) != 0);
+      const uint32_t idesc1 = umma_idesc_f16kind(128, BN, (a.operand_f16 & 2) != 0, (a.operand_f16 & 8) != 0);
+      const int kb_seg0 = a.taps[0] * a.cblks[0];
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -123,6 +125,7 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+          const uint32_t idesc = kb < kb_seg0 ? idesc0 : idesc1;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) per 64-channel block
@@ -262,7 +265,9 @@ int advs_conv_sm100_stats_parts(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
   int tw = largest_divisor_leq(W, 128);
   int th = largest_divisor_leq(H, 128 / tw);
-  if (th == H && tw == W && 128 / (tw * th) > 1 && B > 1) return 0;   // a tile would span images
+  // an image smaller than one tile: tiles span images when B > 1.  The answer must not depend on B (the statistics
+  // path decides the fp32 summation order, and results are bit-reproducible across batch sizes), so B = 1 says 0 too
+  if (th == H && tw == W && 128 / (tw * th) > 1) return 0;
   return (W / tw) * (H / th);
 }
 
@@ -316,6 +321,13 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   a.stats_off = a.up ? (p->up_phase - 1) * a.stats_tpi : 0;
   a.stats = p->stats_partial;
   a.stats_gran = p->stats_gran == 4 ? 4 : 1;
+  a.operand_f16 = p->operand_f16;
+  ADVS_CHECK_ARG((p->operand_f16 & ~15) == 0, "conv_sm100_plan: operand_f16 has unknown bits");
+  // tcgen05.mma kind::f16 with different A and B formats is an illegal instruction on sm_100 (tools/gpu/probe_mixed_mma.py)
+  ADVS_CHECK_ARG(((p->operand_f16 & 1) != 0) == ((p->operand_f16 & 4) != 0),
+                 "conv_sm100_plan: segment 0 activations and weights must have the same 16-bit format");
+  ADVS_CHECK_ARG(p->nseg == 1 || ((p->operand_f16 & 2) != 0) == ((p->operand_f16 & 8) != 0),
+                 "conv_sm100_plan: shortcut activations and weights must have the same 16-bit format");
   if (a.stats) {
     ADVS_CHECK_ARG(p->stats_gran == 0 || p->stats_gran == 1 || p->stats_gran == 4, "conv_sm100_plan: stats_gran must be 0, 1 or 4");
     ADVS_CHECK_ARG(p->out_mode == 0, "conv_sm100_plan: stats_partial needs out_mode 0");

@@ -126,7 +126,9 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader) {   // the whole warp walks the schedule; one elected lane issues (warp-uniform control flow)
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      const uint32_t idesc0 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 1) != 0, (a.operand_f16 & 4) != 0);
+      const uint32_t idesc1 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 2) != 0, (a.operand_f16 & 8) != 0);
+      const int kb_seg0 = a.taps[0] * a.cblks[0];
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -141,6 +143,7 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
+          const uint32_t idesc = kb < kb_seg0 ? idesc0 : idesc1;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)

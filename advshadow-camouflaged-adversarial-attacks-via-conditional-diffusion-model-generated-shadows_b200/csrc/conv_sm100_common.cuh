@@ -25,6 +25,7 @@ struct ConvArgs {
   int stats_tpi, stats_rpi, stats_off;   // row = (m_tile / tpi) * rpi + off + m_tile % tpi
   int stats_gran;                        // 1: one {sum, sumsq} per channel; 4: per 4 consecutive channels
   int up_a, up_b, up;                    // upsample phase: output pixel (2h+a, 2w+b); up = 0/1
+  int operand_f16;                       // advs_conv_params.operand_f16 (bits 0/1: A of segment 0 / 1..2, bits 2/3: B of segment 0 / 1..2)
   EpilogueParams epi;
 };
 

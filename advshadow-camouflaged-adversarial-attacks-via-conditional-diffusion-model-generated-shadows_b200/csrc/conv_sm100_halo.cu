@@ -136,7 +136,8 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader) {   // the whole warp walks the schedule; one elected lane issues (warp-uniform control flow)
-      constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+      const uint32_t idesc0 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 1) != 0, (a.operand_f16 & 4) != 0);
+      const uint32_t idesc1 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 2) != 0, (a.operand_f16 & 8) != 0);
       int stage = 0, abuf = 0;
       uint32_t phase = 0, aphase = 0;
       int acc = 0;
@@ -151,6 +152,7 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
         uint32_t first = 1;
         for (int s = 0; s < a.nseg; ++s) {
           const int taps = a.taps[s];
+          const uint32_t idesc = s == 0 ? idesc0 : idesc1;
           for (int cb = 0; cb < a.cblks[s]; ++cb) {
             mbar_wait(&a_full[abuf], aphase);
             const uint32_t a_base = smem_u32(smem + abuf * Cfg::a_buf_bytes);

@@ -64,7 +64,23 @@ __global__ void k_pack_conv_weight(const float* __restrict__ w, T* __restrict__ 
 // CIN > 0: compile-time channel count; CIN = 0: run-time Cin (<= 7).
 constexpr int kStemPixPerBlock = 256;
 constexpr int kStemPitch = 144;
-template <int CIN>
+// F16: the rows are fp16 pairs instead of bf16 pairs (the sampler state is bounded: |x_t| stays within a few units),
+// to go with fp16 stem weights -- tcgen05 wants both operands of an MMA in the same 16-bit format.
+template <bool F16>
+__device__ __forceinline__ uint32_t stem_pack2(float a, float b) {
+  if constexpr (F16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    return pack_bf16x2(a, b);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ float stem_round(float v) {
+  if constexpr (F16) return __half2float(__float2half_rn(v));
+  else return __bfloat162float(__float2bfloat16_rn(v));
+}
+template <int CIN, bool F16 = false>
 __global__ void __launch_bounds__(kStemPixPerBlock)
 k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int H, int W, int cin_rt, int parts) {
   __shared__ __align__(16) uint8_t rows[kStemPixPerBlock * kStemPitch];
@@ -93,12 +109,12 @@ k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int 
 #pragma unroll
       for (int i = 0; i < 9 * CIN; ++i) {
         e[i] = v[i];
-        if (18 * CIN <= 64) e[9 * CIN + i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+        if (18 * CIN <= 64) e[9 * CIN + i] = v[i] - stem_round<F16>(v[i]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        reinterpret_cast<uint4*>(row)[i] = make_uint4(pack_bf16x2(e[8 * i], e[8 * i + 1]), pack_bf16x2(e[8 * i + 2], e[8 * i + 3]),
-                                                      pack_bf16x2(e[8 * i + 4], e[8 * i + 5]), pack_bf16x2(e[8 * i + 6], e[8 * i + 7]));
+        reinterpret_cast<uint4*>(row)[i] = make_uint4(stem_pack2<F16>(e[8 * i], e[8 * i + 1]), stem_pack2<F16>(e[8 * i + 2], e[8 * i + 3]),
+                                                      stem_pack2<F16>(e[8 * i + 4], e[8 * i + 5]), stem_pack2<F16>(e[8 * i + 6], e[8 * i + 7]));
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(row)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -107,9 +123,10 @@ k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int 
         const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
         for (int ci = 0; ci < Cin; ++ci) {
           const float val = in ? __ldg(x + (((size_t)b * Cin + ci) * H + hh) * W + ww) : 0.f;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(val);
-          row[tap * Cin + ci] = hi;
-          if (parts > 1) row[k9 + tap * Cin + ci] = __float2bfloat16_rn(val - __bfloat162float(hi));
+          const float hif = stem_round<F16>(val);
+          uint16_t* r16 = reinterpret_cast<uint16_t*>(row);
+          r16[tap * Cin + ci] = (uint16_t)(stem_pack2<F16>(hif, 0.f) & 0xFFFFu);
+          if (parts > 1) r16[k9 + tap * Cin + ci] = (uint16_t)(stem_pack2<F16>(val - hif, 0.f) & 0xFFFFu);
         }
       }
     }
@@ -126,14 +143,15 @@ k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int 
 }
 
 // matching weight rows [O][64]: both parts carry bf16(w[o][ci][tap])
-__global__ void k_pack_stem_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int O, int I, int parts) {
+template <typename T>
+__global__ void k_pack_stem_weight(const float* __restrict__ w, T* __restrict__ dst, int O, int I, int parts) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)O * 64) return;
   const int o = (int)(idx >> 6), slot = (int)(idx & 63);
   const int k9 = 9 * I;
   const int part = slot / k9, r = slot - part * k9;
   const int tap = r / I, ci = r - tap * I;
-  dst[idx] = __float2bfloat16_rn(part < parts ? w[((size_t)o * I + ci) * 9 + tap] : 0.f);
+  dst[idx] = from_f<T>(part < parts ? w[((size_t)o * I + ci) * 9 + tap] : 0.f);
 }
 
 template <typename T>
@@ -394,6 +412,8 @@ int advs_pack_conv_weight(const float* w, void* dst, int O, int I, int kh, int k
     k_pack_conv_weight<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (float*)dst, O, I, kh * kw);
   else if (dtype == ADVS_BF16)
     k_pack_conv_weight<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, O, I, kh * kw);
+  else if (dtype == ADVS_F16)
+    k_pack_conv_weight<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)dst, O, I, kh * kw);
   else
     ADVS_CHECK_ARG(false, "pack_conv_weight: bad dtype");
   ADVS_CHECK_LAUNCH("pack_conv_weight");
@@ -408,32 +428,53 @@ int advs_pack_upconv_weight(const float* w, void* dst, int O, int I, int dtype, 
     k_pack_upconv_weight<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (float*)dst, O, I);
   else if (dtype == ADVS_BF16)
     k_pack_upconv_weight<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, O, I);
+  else if (dtype == ADVS_F16)
+    k_pack_upconv_weight<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)dst, O, I);
   else
     ADVS_CHECK_ARG(false, "pack_upconv_weight: bad dtype");
   ADVS_CHECK_LAUNCH("pack_upconv_weight");
   return ADVS_OK;
 }
 
-int advs_stem_im2col(const float* x, void* col, int B, int H, int W, int Cin, void* stream) {
+int advs_stem_im2col_ex(const float* x, void* col, int B, int H, int W, int Cin, int dtype, void* stream) {
   ADVS_CHECK_ARG(x && col && B > 0 && H > 0 && W > 0 && Cin > 0 && 9 * Cin <= 64, "stem_im2col: bad args (needs 9*Cin <= 64)");
+  ADVS_CHECK_ARG(dtype == ADVS_BF16 || dtype == ADVS_F16, "stem_im2col: dtype must be ADVS_BF16 or ADVS_F16");
   const size_t npix = (size_t)B * H * W;
   const unsigned blocks = (unsigned)((npix + kStemPixPerBlock - 1) / kStemPixPerBlock);
-  if (Cin == 3)
-    k_stem_im2col<3><<<blocks, kStemPixPerBlock, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin, 2);
-  else
-    k_stem_im2col<0><<<blocks, kStemPixPerBlock, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)col, B, H, W, Cin,
-                                                                         18 * Cin <= 64 ? 2 : 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* c = (__nv_bfloat16*)col;
+  const int parts = 18 * Cin <= 64 ? 2 : 1;
+  if (Cin == 3) {
+    if (dtype == ADVS_F16) k_stem_im2col<3, true><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, 2);
+    else k_stem_im2col<3, false><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, 2);
+  } else {
+    if (dtype == ADVS_F16) k_stem_im2col<0, true><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, parts);
+    else k_stem_im2col<0, false><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, parts);
+  }
   ADVS_CHECK_LAUNCH("stem_im2col");
   return ADVS_OK;
 }
 
-int advs_pack_stem_weight(const float* w, void* dst, int O, int I, void* stream) {
+int advs_stem_im2col(const float* x, void* col, int B, int H, int W, int Cin, void* stream) {
+  return advs_stem_im2col_ex(x, col, B, H, W, Cin, ADVS_BF16, stream);
+}
+
+int advs_pack_stem_weight_ex(const float* w, void* dst, int O, int I, int dtype, void* stream) {
   ADVS_CHECK_ARG(w && dst && O > 0 && I > 0 && 9 * I <= 64, "pack_stem_weight: bad args (needs 9*I <= 64)");
+  ADVS_CHECK_ARG(dtype == ADVS_BF16 || dtype == ADVS_F16, "pack_stem_weight: dtype must be ADVS_BF16 or ADVS_F16");
   const size_t n = (size_t)O * 64;
-  k_pack_stem_weight<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, O, I,
-                                                                                    18 * I <= 64 ? 2 : 1);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const int parts = 18 * I <= 64 ? 2 : 1;
+  if (dtype == ADVS_F16)
+    k_pack_stem_weight<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__half*)dst, O, I, parts);
+  else
+    k_pack_stem_weight<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)dst, O, I, parts);
   ADVS_CHECK_LAUNCH("pack_stem_weight");
   return ADVS_OK;
+}
+
+int advs_pack_stem_weight(const float* w, void* dst, int O, int I, void* stream) {
+  return advs_pack_stem_weight_ex(w, dst, O, I, ADVS_BF16, stream);
 }
 
 int advs_conv3x3_stem(const float* x, const float* w, const float* bias, void* y, int B, int H, int W, int Cin,

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ p
 
 // thread = one 8-channel vector position, looping over the pixels of its chunk: the 16 scale/shift
 // floats stay in registers, so the stream is exactly one 16-byte load + one 16-byte store per vector.
-template <typename T, bool SILU, bool WIDE = false>
+template <typename T, bool SILU, bool WIDE = false, bool OUT_F16 = false>
 __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict__ x1, int c1, int HW,
                            int pix_per_chunk, const float* __restrict__ scale_shift, T* __restrict__ y,
                            const uint8_t* __restrict__ lo0 = nullptr, const uint8_t* __restrict__ lo1 = nullptr) {
@@ -229,7 +229,13 @@ __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict
       f[i] = a;
     }
     Vec8<T> vo;
-    vo.from_float(f);
+    if constexpr (OUT_F16 && sizeof(T) == 2) {   // fp16 GEMM operand: same 16 bits, three more of them mantissa
+      __half2* h = reinterpret_cast<__half2*>(&vo.v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    } else {
+      vo.from_float(f);
+    }
     vo.store_stream(dst + (size_t)p * Ctot);
   };
   int p = p0 + pl;
@@ -305,18 +311,23 @@ static int gn_apply_impl(const void* x0, int c0, const void* x1, int c1, int B, 
 }
 
 static int gn_apply_wide_impl(const void* x0, const void* lo0, int c0, const void* x1, const void* lo1, int c1, int B, int HW,
-                              const float* ss, int silu, void* y, cudaStream_t st) {
+                              const float* ss, int silu, void* y, bool out_f16, cudaStream_t st) {
   using T = __nv_bfloat16;
   GnGeom g = gn_geom(B, HW);
   int cv = (c0 + c1) / 8;
   int threads = cv <= 256 ? 256 : 1024;
   dim3 grid(g.chunks, B);
-  if (silu)
-    k_gn_apply<T, true, true><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y,
-                                                        (const uint8_t*)lo0, (const uint8_t*)lo1);
-  else
-    k_gn_apply<T, false, true><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y,
-                                                         (const uint8_t*)lo0, (const uint8_t*)lo1);
+  const bool wide = lo0 || lo1;
+#define ADVS_GN(S, W_, F) k_gn_apply<T, S, W_, F><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, \
+                                                                        ss, (T*)y, (const uint8_t*)lo0, (const uint8_t*)lo1)
+  if (silu) {
+    if (wide) { if (out_f16) ADVS_GN(true, true, true); else ADVS_GN(true, true, false); }
+    else { if (out_f16) ADVS_GN(true, false, true); else ADVS_GN(true, false, false); }
+  } else {
+    if (wide) { if (out_f16) ADVS_GN(false, true, true); else ADVS_GN(false, true, false); }
+    else { if (out_f16) ADVS_GN(false, false, true); else ADVS_GN(false, false, false); }
+  }
+#undef ADVS_GN
   ADVS_CHECK_LAUNCH("groupnorm_apply_wide");
   return ADVS_OK;
 }
@@ -397,15 +408,14 @@ int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, 
 }
 
 int advs_groupnorm_apply_wide(const void* x0, const void* lo0, int c0, const void* x1, const void* lo1, int c1, int B,
-                              int HW, const float* scale_shift, int silu, void* y, void* stream) {
+                              int HW, const float* scale_shift, int silu, void* y, int y_dtype, void* stream) {
+  ADVS_CHECK_ARG(y_dtype == ADVS_BF16 || y_dtype == ADVS_F16, "groupnorm_apply_wide: y_dtype must be ADVS_BF16 or ADVS_F16");
   ADVS_CHECK_ARG(x0 && c0 > 0 && B > 0 && HW > 0 && scale_shift && y, "groupnorm_apply_wide: bad args");
   if (!x1) { c1 = 0; lo1 = nullptr; }
   ADVS_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0, "groupnorm_apply_wide: channel counts must be multiples of 8");
   ADVS_CHECK_ARG((c0 + c1) / 8 <= 1024, "groupnorm_apply_wide: at most 8192 channels");
   ADVS_CHECK_ARG(((uintptr_t)lo0 | (uintptr_t)lo1) % 8 == 0, "groupnorm_apply_wide: lo pointers must be 8-byte aligned");
-  if (!lo0 && !lo1)
-    return gn_apply_impl<__nv_bfloat16>(x0, c0, x1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
-  return gn_apply_wide_impl(x0, lo0, c0, x1, lo1, c1, B, HW, scale_shift, silu, y, (cudaStream_t)stream);
+  return gn_apply_wide_impl(x0, lo0, c0, x1, lo1, c1, B, HW, scale_shift, silu, y, y_dtype == ADVS_F16, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -237,6 +237,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major
+// kind::f16 with the operand formats chosen per operand: format code 0 = fp16, 1 = bf16 (A: bits [7,10), B: [10,13))
+__host__ __device__ constexpr uint32_t umma_idesc_f16kind(int M, int N, bool a_is_f16, bool b_is_f16) {
+  return (1u << 4) | ((a_is_f16 ? 0u : 1u) << 7) | ((b_is_f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4)                    // D format F32
          | (1u << 7)                  // A format BF16

@@ -16,6 +16,7 @@ from .plan import Plan, UNetSpec, build_unet_plan
 
 _DT = {"fp32": capi.F32, "bf16": capi.BF16}
 _TORCH_DT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+_CAPI_DT = {torch.float32: capi.F32, torch.bfloat16: capi.BF16, torch.float16: capi.F16}
 
 
 def _stream_ptr():
@@ -27,13 +28,20 @@ class UNetEngine:
 
     def __init__(self, spec: UNetSpec, params: Dict[str, torch.Tensor], B: int, H: int, W: int,
                  precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto", fuse_gn_stats: bool = True,
-                 fuse_upsample: bool = True, wide_prenorm: int = 2):
+                 fuse_upsample: bool = True, wide_prenorm: int = 2, gemm_operands: str = "fp16"):
         """`wide_prenorm`: bf16 mode only -- tensors of the `wide_prenorm` highest-resolution levels that a GroupNorm
         reads (residual stream, conv1 outputs, skips) are stored as bf16 + an int8 mantissa extension
         (advs_conv_params.y_lo), so the value entering the normalisation carries 16 mantissa bits like the
         reference's fp32 tensor (dm1:71-72, 83-84) and the GEMM operand is rounded once instead of twice.  These
         levels have the fewest channels per dot product, hence the least averaging of rounding noise: the error
-        study in DESIGN.md attributes 90 % of the bf16-mode output variance to them.  0 disables."""
+        study in DESIGN.md attributes 90 % of the bf16-mode output variance to them.  0 disables.
+        `gemm_operands`: "fp16" (default) | "bf16" -- the 16-bit format of the GEMM operands that are bounded by
+        construction: GroupNorm outputs (|y| <= sqrt(group size)*|gamma| + |beta|) and the weights multiplying them.
+        fp16 gives them 11 mantissa bits instead of 8 at the same tcgen05 rate (kind::f16 takes either format);
+        the stem's im2col rows of the (bounded) sampler state are fp16 too.  Activations whose range is not bounded
+        -- conv outputs, the residual stream, q/k/v, attention output -- stay bf16, and so do the weights multiplying
+        them: the hardware rejects an MMA whose two operands differ in format (tools/gpu/probe_mixed_mma.py:
+        illegal instruction).  "bf16" makes every operand bf16."""
         if precision not in _DT:
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         any_p = next(iter(params.values()))
@@ -54,6 +62,9 @@ class UNetEngine:
         if (conv_impl == "sm100" or attn_impl == "sm100") and precision != "bf16":
             raise ValueError("the tcgen05 kernels are bf16-only; use precision='bf16'")
         self.conv_impl, self.attn_impl = conv_impl, attn_impl
+        if gemm_operands not in ("fp16", "bf16"):
+            raise ValueError("gemm_operands must be 'fp16' or 'bf16'")
+        self.gemm_operands = gemm_operands if (precision == "bf16" and conv_impl == "sm100") else "bf16"
 
         # Upsample + conv3x3 as four low-res 2x2 phase convs (tcgen05 path only; fp32 mode keeps the
         # reference's op order: nearest upsample, then the 3x3 conv)
@@ -99,6 +110,16 @@ class UNetEngine:
                 name = plan.new_buf("gnpart", (B, parts, a["cout"] // gran, 2), "f32")
                 plan.bufs[name].first, plan.bufs[name].last = idx, plan.bufs[a["dst"]].last
                 self._stat_buf[a["dst"]] = (name, parts, gran)
+        # fp16 GEMM operands: a GroupNorm output is fp16 when its (single) consumer is a tcgen05 conv / the head
+        self._gn_f16 = set()
+        if self.gemm_operands == "fp16":
+            gn_dst = {op.args["dst"] for op in plan.ops if op.kind == "gn"}
+            for op in plan.ops:
+                a = op.args
+                if op.kind == "conv" and self._conv_sm100_ok(a) and a["segs"][0][0] in gn_dst:
+                    self._gn_f16.add(a["segs"][0][0])
+                elif op.kind == "head" and self._head_sm100_ok(a) and a["src"] in gn_dst:
+                    self._gn_f16.add(a["src"])
         # "wide" pre-norm storage: an int8 companion (same lifetime) for every conv output of the top levels
         # that a GroupNorm reads
         self._lo_buf = {}
@@ -165,10 +186,32 @@ class UNetEngine:
     def _ptr(self, buf):
         return self.arena.data_ptr() + self.plan.bufs[buf].offset
 
+    def _w_dtype(self, src, on_sm100=True):
+        """storage format of the packed weights that multiply activation buffer `src` on the tcgen05 path"""
+        if self.gemm_operands == "fp16" and on_sm100 and (src in self._gn_f16 or src == "stem_col"):
+            return torch.float16
+        return _TORCH_DT[self.precision]
+
+    def _operand_bits(self, srcs, dtypes):
+        """advs_conv_params.operand_f16 from the activation buffers / packed-weight dtypes of segment 0 and 1.."""
+        bits = 0
+        f16 = lambda s_: s_ in self._gn_f16 or (s_ == "stem_col" and self.gemm_operands == "fp16")
+        if f16(srcs[0]):
+            bits |= 1
+        if any(f16(s_) for s_ in srcs[1:]):
+            bits |= 2
+        if dtypes[0] == torch.float16:
+            bits |= 4
+        if any(d == torch.float16 for d in dtypes[1:]):
+            bits |= 8
+        return bits
+
     def buffer_view(self, buf):
         """torch view of an arena buffer (debug / tests)."""
         b = self.plan.bufs[buf]
         dt = {"act": _TORCH_DT[self.precision], "f32": torch.float32, "u8": torch.int8}[b.kind]
+        if buf in self._gn_f16:
+            dt = torch.float16
         n = b.elems * {"act": self.act_bytes, "f32": 4, "u8": 1}[b.kind]
         return self.arena[b.offset:b.offset + n].view(dt).view(*[s for s in b.shape if not isinstance(s, str)])
 
@@ -180,7 +223,7 @@ class UNetEngine:
             a = op.args
             if op.kind == "stem":
                 if self._stem_sm100_ok(a):
-                    self._packed[(a["weight"], "stem64")] = torch.empty(a["cout"], 1, 64, dtype=tdt, device=dev)
+                    self._packed[(a["weight"], "stem64")] = torch.empty(a["cout"], 1, 64, dtype=self._w_dtype("stem_col"), device=dev)
                     self._stem_col = torch.empty(self.B, a["H"], a["W"], 64, dtype=tdt, device=dev)
                 else:
                     self._packed[(a["weight"], None)] = torch.empty(a["cout"], 9, a["cin"], dtype=torch.float32, device=dev)
@@ -189,16 +232,18 @@ class UNetEngine:
                 # the head runs through the implicit-GEMM conv (fp32 NCHW epilogue); on the tcgen05 path
                 # its 3 output channels are zero-padded to one 64-row weight tile
                 pad = 64 if self._head_sm100_ok(a) else a["cout"]
-                self._packed[(a["weight"], None)] = torch.zeros(pad, 9, a["cin"], dtype=tdt, device=dev)
+                wdt = self._w_dtype(a["src"], self._head_sm100_ok(a))
+                self._packed[(a["weight"], None)] = torch.zeros(pad, 9, a["cin"], dtype=wdt, device=dev)
                 self._bias[(a["weight"],)] = torch.zeros(pad, dtype=torch.float32, device=dev)
             elif op.kind == "conv":
                 for (src, wname, taps, sl) in a["segs"]:
                     c = self.plan.shape(src)[3]
-                    self._packed[(wname, sl)] = torch.empty(a["cout"], taps, c, dtype=tdt, device=dev)
+                    wdt = self._w_dtype(src, self._conv_sm100_ok(a))
+                    self._packed[(wname, sl)] = torch.empty(a["cout"], taps, c, dtype=wdt, device=dev)
                 if a["bias"]:
                     self._bias[tuple(a["bias"])] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
             elif op.kind == "upconv":
-                self._packed[(a["weight"], "up4")] = torch.empty(4, a["cout"], 4, a["C"], dtype=tdt, device=dev)
+                self._packed[(a["weight"], "up4")] = torch.empty(4, a["cout"], 4, a["C"], dtype=self._w_dtype(a["src"]), device=dev)
                 self._bias[(a["weight"],)] = torch.empty(a["cout"], dtype=torch.float32, device=dev)
         ted = spec.time_embed_dim
         self.temb_w = torch.empty(self.plan.temb_total, ted, dtype=torch.float32, device=dev)
@@ -238,16 +283,16 @@ class UNetEngine:
                 w = p32(wname + ".weight")
                 if sl == "up4":
                     capi.call("advs_pack_upconv_weight", w.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1],
-                              capi.BF16 if dst.dtype == torch.bfloat16 else capi.F32, st)
+                              _CAPI_DT[dst.dtype], st)
                     continue
                 if sl == "stem64":
-                    capi.call("advs_pack_stem_weight", w.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1], st)
+                    capi.call("advs_pack_stem_weight_ex", w.data_ptr(), dst.data_ptr(), w.shape[0], w.shape[1],
+                              _CAPI_DT[dst.dtype], st)
                     continue
                 if sl is not None:
                     w = w[:, sl[0]:sl[1]].contiguous()
                 O, I, kh, kw = w.shape          # dst may have more (zero) rows than O: the padded head
-                dt = capi.F32 if dst.dtype == torch.float32 else capi.BF16
-                capi.call("advs_pack_conv_weight", w.data_ptr(), dst.data_ptr(), O, I, kh, kw, dt, st)
+                capi.call("advs_pack_conv_weight", w.data_ptr(), dst.data_ptr(), O, I, kh, kw, _CAPI_DT[dst.dtype], st)
             for names, dst in self._bias.items():
                 acc = p32(names[0] + ".bias").clone()
                 for n in names[1:]:
@@ -279,12 +324,13 @@ class UNetEngine:
             a = op.args
             if op.kind == "stem" and self._stem_sm100_ok(a):
                 w, b = self._packed[(a["weight"], "stem64")], self._bias[(a["weight"],)]
-                L.append((lib.advs_stem_im2col, (self.x.data_ptr(), self._stem_col.data_ptr(), B, a["H"], a["W"], a["cin"]),
-                          "stem_im2col"))
+                L.append((lib.advs_stem_im2col_ex, (self.x.data_ptr(), self._stem_col.data_ptr(), B, a["H"], a["W"], a["cin"],
+                                                    _CAPI_DT[w.dtype]), "stem_im2col"))
                 cp = capi.ConvParams()
                 cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], a["cout"], 1, 1
                 cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = self._stem_col.data_ptr(), w.data_ptr(), 64, 1
                 cp.bias, cp.out_mode, cp.y, cp.dtype = b.data_ptr(), 0, self._ptr(a["dst"]), dt
+                cp.operand_f16 = self._operand_bits(["stem_col"], [w.dtype])
                 if a["dst"] in self._stat_buf:
                     cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
                     cp.stats_gran = self._stat_buf[a["dst"]][2]
@@ -309,6 +355,7 @@ class UNetEngine:
                 cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = self._ptr(a["src"]), w.data_ptr(), a["cin"], 9
                 cp.bias = b.data_ptr()
                 cp.out_mode, cp.y, cp.cout_valid, cp.dtype = 2, self.eps.data_ptr(), a["cout"], dt
+                cp.operand_f16 = self._operand_bits([a["src"]], [w.dtype])
                 self._keep.append(cp)
                 if self._head_sm100_ok(a):
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
@@ -342,9 +389,10 @@ class UNetEngine:
                                                            a["groups"], 1e-5, g.data_ptr(), bt.data_ptr(), self._ptr(a["ss"])),
                           "gn_finalize"))
                 los = [self._ptr(self._lo_buf[sn]) if sn in self._lo_buf else None for sn in srcs] + [None]
-                if los[0] or los[1]:
+                if los[0] or los[1] or a["dst"] in self._gn_f16:
                     L.append((lib.advs_groupnorm_apply_wide, (x0, los[0], c0, x1, los[1], c1, B, a["HW"], self._ptr(a["ss"]),
-                                                              1 if a["silu"] else 0, self._ptr(a["dst"])), "gn_apply"))
+                                                              1 if a["silu"] else 0, self._ptr(a["dst"]),
+                                                              capi.F16 if a["dst"] in self._gn_f16 else capi.BF16), "gn_apply"))
                 else:
                     L.append((lib.advs_groupnorm_apply, (x0, c0, x1, c1, B, a["HW"], self._ptr(a["ss"]),
                                                          1 if a["silu"] else 0, self._ptr(a["dst"]), dt), "gn_apply"))
@@ -376,6 +424,8 @@ class UNetEngine:
                     cp.stats_gran = self._stat_buf[a["dst"]][2]
                 if a["dst"] in self._lo_buf:
                     cp.y_lo = self._ptr(self._lo_buf[a["dst"]])
+                cp.operand_f16 = self._operand_bits([sg[0] for sg in a["segs"]],
+                                                    [self._packed[(sg[1], sg[3])].dtype for sg in a["segs"]])
                 self._keep.append(cp)
                 if self._conv_sm100_ok(a):
                     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
@@ -408,6 +458,7 @@ class UNetEngine:
                     cp.B, cp.H, cp.W, cp.Cout, cp.stride, cp.nseg = B, a["H"], a["W"], a["cout"], 1, 1
                     cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = self._ptr(a["src"]), w4[ph].data_ptr(), a["C"], 4
                     cp.bias, cp.out_mode, cp.y, cp.dtype, cp.up_phase = b.data_ptr(), 0, self._ptr(a["dst"]), dt, ph + 1
+                    cp.operand_f16 = self._operand_bits([a["src"]], [w4.dtype])
                     if a["dst"] in self._stat_buf:
                         cp.stats_partial = self._ptr(self._stat_buf[a["dst"]][0])
                         cp.stats_gran = self._stat_buf[a["dst"]][2]
@@ -528,13 +579,17 @@ class UNetEngine:
         assert len(out) == len(self._launches)
         return out
 
-    def profile_forward(self, repeats=1):
-        """Run the forward eagerly with a CUDA-event pair around every launch (on the launching stream).
-        Returns {name: dict(ms, flops, bytes, launches)} summed over the forward, averaged over repeats."""
+    def profile_forward(self, repeats=1, warmup=0, per_repeat=None):
+        """Run the forward eagerly with a CUDA-event pair around every launch (on the launching stream); launches are
+        queued back to back, the host only synchronises once per repeat.  Returns {name: dict(ms, flops, bytes,
+        launches)} summed over the forward and averaged over `repeats` (after `warmup` untimed repeats); with
+        `per_repeat=<name>` also the list of that class's summed ms in every repeat (for min / median)."""
         costs = self.launch_costs()
         st = _stream_ptr()
-        agg = {}
+        agg, series = {}, []
         with torch.cuda.device(self.device):
+            for _ in range(warmup):
+                self.run()
             for _ in range(repeats):
                 evs = []
                 for (fn, args, name) in self._launches:
@@ -546,10 +601,15 @@ class UNetEngine:
                         raise capi.AdvsError(f"{name} failed: {self.lib.advs_last_error().decode()}")
                     evs.append((e0, e1))
                 torch.cuda.synchronize(self.device)
+                tot = 0.0
                 for (e0, e1), (name, fl, by) in zip(evs, costs):
                     d = agg.setdefault(name, dict(ms=0.0, flops=0, bytes=0, launches=0))
-                    d["ms"] += e0.elapsed_time(e1) / repeats
+                    ms = e0.elapsed_time(e1)
+                    if name == per_repeat:
+                        tot += ms
+                    d["ms"] += ms / repeats
                     d["flops"] += fl / repeats
                     d["bytes"] += by / repeats
                     d["launches"] += 1.0 / repeats
-        return agg
+                series.append(tot)
+        return (agg, series) if per_repeat is not None else agg

@@ -23,6 +23,8 @@ def _dt(t):
         return capi.F32
     if t.dtype == torch.bfloat16:
         return capi.BF16
+    if t.dtype == torch.float16:
+        return capi.F16
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 

@@ -33,6 +33,10 @@ extern "C" {
 
 #define ADVS_F32 0
 #define ADVS_BF16 1
+/* fp16 is an OPERAND format only (packed weights, GroupNorm outputs): values that are bounded by construction keep
+ * three more mantissa bits than in bf16 at the same tensor-core rate (tcgen05 kind::f16 takes either format per
+ * operand); activations whose range is not bounded (conv outputs, the residual stream, q/k/v) stay bf16. */
+#define ADVS_F16 2
 
 #define ADVS_OK 0
 #define ADVS_ERR_ARG (-1)
@@ -59,7 +63,8 @@ int advs_linear_f32(const float* x, const float* w, const float* b, float* y, in
                     int out_f, int silu_in, int silu_out, void* stream);
 
 /* ---- weight packing --------------------------------------------------------------------- */
-/* nn.Conv2d weight OIHW fp32 -> [O][kh*kw][I] in `dtype` (K-major rows for the implicit GEMM). */
+/* nn.Conv2d weight OIHW fp32 -> [O][kh*kw][I] in `dtype` (K-major rows for the implicit GEMM); dtype may be
+ * ADVS_F16 for the tcgen05 path (advs_conv_params.operand_f16 bit 2). */
 int advs_pack_conv_weight(const float* w_oihw, void* dst, int O, int I, int kh, int kw, int dtype,
                           void* stream);
 
@@ -77,7 +82,10 @@ int advs_conv3x3_stem(const float* x_nchw, const float* w, const float* bias, vo
  * rest 0), advs_pack_stem_weight writes the matching bf16 rows [Cout][64]; the stem is then a 1x1 convolution
  * (advs_conv_sm100_plan with one segment, C = 64, taps = 1) with the usual fused epilogue. */
 int advs_stem_im2col(const float* x_nchw, void* col, int B, int H, int W, int Cin, void* stream);
+/* dtype = ADVS_F16: fp16 rows (hi = fp16(x), lo = fp16(x - hi)) for fp16 stem weights; the sampler state is bounded */
+int advs_stem_im2col_ex(const float* x_nchw, void* col, int B, int H, int W, int Cin, int dtype, void* stream);
 int advs_pack_stem_weight(const float* w_oihw, void* dst, int O, int I, void* stream);
+int advs_pack_stem_weight_ex(const float* w_oihw, void* dst, int O, int I, int dtype, void* stream); /* ADVS_BF16 | ADVS_F16 */
 /* x NHWC `dtype` [B,H,W,Cin], w fp32 [Cout][9][Cin], y NCHW fp32 [B,Cout,H,W]. 3x3, pad 1. */
 int advs_conv3x3_head(const void* x, const float* w, const float* bias, float* y_nchw, int B,
                       int H, int W, int Cin, int Cout, int dtype, void* stream);
@@ -111,7 +119,9 @@ int advs_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int B, 
 /* bf16 only: same, where lo0 / lo1 (each may be NULL) are the int8 mantissa extensions written by a conv epilogue
  * through advs_conv_params.y_lo for x0 / x1. */
 int advs_groupnorm_apply_wide(const void* x0, const void* lo0, int c0, const void* x1, const void* lo1, int c1, int B,
-                              int HW, const float* scale_shift, int silu, void* y, void* stream);
+                              int HW, const float* scale_shift, int silu, void* y, int y_dtype, void* stream);
+/* y_dtype: ADVS_BF16, or ADVS_F16 when the consumer is a tcgen05 conv with operand_f16 bit 0 set (a normalised
+ * tensor is bounded by sqrt(group size) * |gamma| + |beta|, far inside the fp16 range). */
 
 /* ---- K1/K2/K3: convolution as implicit GEMM (dm1:73, 86, 90, 114-115, 134, 148) ----------- */
 /* D[pixel, cout] = sum over K-segments s, taps, channels of  X_s[pixel + tap, c] * W_s[cout, tap, c]
@@ -171,6 +181,10 @@ typedef struct advs_conv_params {
    * advs_groupnorm_apply_wide reads the pair, so the normalised GEMM operand is rounded once instead of twice
    * (the reference normalises fp32 tensors, dm1:71-72, 83-84). */
   void* y_lo;
+  /* sm100 path: which GEMM operands are fp16 instead of bf16 (ADVS_F16 above): bit 0 = the activations of segment 0
+   * (a GroupNorm output written by advs_groupnorm_apply_wide with y_dtype = ADVS_F16), bit 1 = the activations of
+   * segments 1..2, bit 2 = the packed weights of segment 0, bit 3 = the packed weights of segments 1..2. */
+  int32_t operand_f16;
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */

@@ -129,10 +129,10 @@ def ddim_sample(p, cfg, acp, x_T, n, T=1000, eta=0.0, max_steps=None):   # diff_
     B = x.shape[0]
     done = 0
     for i in reversed(range(n)):
-        t = torch.full((B,), int(seq[i]), dtype=torch.long)
-        a_t = acp[int(seq[i])].float().reshape(1, 1, 1, 1)
-        a_p = acp[int(prev[i])].float().reshape(1, 1, 1, 1)
-        x = ddim_update(x, unet_forward(p, cfg, x, t), a_t, a_p, eta)
+        t = torch.full((B,), int(seq[i]), dtype=torch.long, device=x.device)
+        a_t = acp[int(seq[i])].float().reshape(1, 1, 1, 1).to(x.device)
+        a_p = acp[int(prev[i])].float().reshape(1, 1, 1, 1).to(x.device)
+        x = ddim_update(x, unet_forward(p, cfg, x, t).float(), a_t, a_p, eta)
         done += 1
         if max_steps and done >= max_steps:
             break
@@ -141,13 +141,15 @@ def ddim_sample(p, cfg, acp, x_T, n, T=1000, eta=0.0, max_steps=None):   # diff_
 
 def gaussian_blur5(mask):                                                # tools/train_shadow.py:147-153
     """cv2.GaussianBlur(mask,(5,5),0): fixed [1,4,6,4,1]/16 table, BORDER_REFLECT_101."""
-    k = torch.tensor([1., 4., 6., 4., 1.]) / 16
+    k = (torch.tensor([1., 4., 6., 4., 1.]) / 16).to(mask.device)
     m = F.pad(mask[None, None], (2, 2, 2, 2), mode="reflect")
     return F.conv2d(F.conv2d(m, k.view(1, 1, 1, 5)), k.view(1, 1, 5, 1))[0, 0]
 
 
 def create_shadow_mask(H, W, center, radius):                            # ddim2/diff_model2.py:552-570
     Y, X = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+    if torch.is_tensor(center):
+        Y, X = Y.to(center.device), X.to(center.device)
     return (torch.sqrt((X - center[0]) ** 2 + (Y - center[1]) ** 2) <= radius).float()
 
 

@@ -31,10 +31,32 @@ def temb_table(plan, params, timesteps):
     return torch.cat(cols, 1)
 
 
-def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2):
+def _sm100_ok(plan, a):
+    """engine._conv_sm100_ok restated: which convs run on the tcgen05 path (and may take fp16 operands)"""
+    if a["cout"] % 64 or any(plan.shape(src)[3] % 64 for (src, _, _, _) in a["segs"]):
+        return False
+    return not (a["qkv"] is not None and (a["cout"] // (3 * a["heads"])) % 32)
+
+
+def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2, gemm_operands="fp16", mixed_mma=False,
+             exact_w=()):
     """`wide_prenorm` (with round_bf16): conv outputs of that many top-resolution levels keep an unrounded copy that
-    only GroupNorm reads (the engine's bf16 + int8 mantissa-extension storage, exact to 2^-17)."""
+    only GroupNorm reads (the engine's bf16 + int8 mantissa-extension storage, exact to 2^-17).
+    `gemm_operands` = "fp16": GroupNorm outputs consumed by a tcgen05 conv, and the weights multiplying them, are
+    rounded to fp16 instead of bf16 (engine.UNetEngine(gemm_operands=...)); `mixed_mma`: every other tcgen05
+    conv's weights are fp16 as well (their activations stay bf16) -- the hardware rejects mixed operand formats
+    (tools/gpu/probe_mixed_mma.py), so the engine never does this; kept for the error study.  `exact_w`: weight
+    categories left unrounded ("stem", "shortcut", "upconv", "down", "proj"), same purpose."""
     rnd = (lambda t: t.to(torch.bfloat16).float()) if round_bf16 else (lambda t: t)
+    r16 = (lambda t: t.to(torch.float16).float()) if (round_bf16 and gemm_operands == "fp16") else rnd
+    gn_dst = {op.args["dst"] for op in plan.ops if op.kind == "gn"}
+    gn_f16 = set()
+    for op in plan.ops:
+        a = op.args
+        if op.kind == "conv" and _sm100_ok(plan, a) and a["segs"][0][0] in gn_dst:
+            gn_f16.add(a["segs"][0][0])
+        elif op.kind == "head" and a["cin"] % 64 == 0 and a["src"] in gn_dst:
+            gn_f16.add(a["src"])
     wide = {}
 
     def store(dst, t_nhwc):
@@ -51,14 +73,17 @@ def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2):
     for op in plan.ops:
         a = op.args
         if op.kind == "stem":
-            y = F.conv2d(x, params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
+            # (the engine feeds x as a bf16 hi/lo pair: exact to 2^-17; only the weights are rounded)
+            # fp16 mode: fp16 hi/lo rows of x (exact to 2^-22) x fp16 weights
+            wq = params[a["weight"] + ".weight"] if "stem" in exact_w else r16(params[a["weight"] + ".weight"])
+            y = F.conv2d(x, wq, params[a["weight"] + ".bias"], padding=1)
             store(a["dst"], _nhwc(y))
         elif op.kind == "gn":
             xin = torch.cat([wide.get(s, bufs[s]) for s in a["srcs"]], 3)
             y = F.group_norm(_nchw(xin), a["groups"], params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], 1e-5)
             if a["silu"]:
                 y = F.silu(y)
-            bufs[a["dst"]] = rnd(_nhwc(y))
+            bufs[a["dst"]] = (r16 if a["dst"] in gn_f16 else rnd)(_nhwc(y))
         elif op.kind == "conv":
             acc = None
             for i, (src, wname, taps, sl) in enumerate(a["segs"]):
@@ -66,10 +91,14 @@ def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2):
                 if sl is not None:
                     w = w[:, sl[0]:sl[1]]
                 xi = _nchw(bufs[src])
+                kind = ("shortcut" if i > 0 else "down" if a["stride"] == 2 else "proj" if (taps == 1 and a["residual"]) else "other")
+                wq = (r16 if (src in gn_f16 or (mixed_mma and _sm100_ok(plan, a))) else wr)(w)
+                if kind in exact_w:
+                    wq = w
                 if taps == 9:
-                    y = F.conv2d(xi, wr(w), None, stride=a["stride"] if i == 0 else 1, padding=1)
+                    y = F.conv2d(xi, wq, None, stride=a["stride"] if i == 0 else 1, padding=1)
                 else:
-                    y = F.conv2d(xi, wr(w), None)
+                    y = F.conv2d(xi, wq, None)
                 acc = y if acc is None else acc + y
             for bn in a["bias"]:
                 acc = acc + params[bn + ".bias"][None, :, None, None]
@@ -100,10 +129,12 @@ def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2):
             bufs[a["dst"]] = _nhwc(y)
         elif op.kind == "upconv":
             y = F.interpolate(_nchw(bufs[a["src"]]), scale_factor=2, mode="nearest")
-            y = F.conv2d(y, wr(params[a["weight"] + ".weight"]), params[a["weight"] + ".bias"], padding=1)
+            wq = params[a["weight"] + ".weight"] if "upconv" in exact_w else (r16 if mixed_mma else wr)(params[a["weight"] + ".weight"])
+            y = F.conv2d(y, wq, params[a["weight"] + ".bias"], padding=1)
             store(a["dst"], _nhwc(y))
         elif op.kind == "head":
-            eps = F.conv2d(_nchw(bufs[a["src"]]), params[a["weight"] + ".weight"], params[a["weight"] + ".bias"], padding=1)
+            wq = (r16 if (a["src"] in gn_f16 or mixed_mma) else wr)(params[a["weight"] + ".weight"])
+            eps = F.conv2d(_nchw(bufs[a["src"]]), wq, params[a["weight"] + ".bias"], padding=1)
         else:
             raise AssertionError(op.kind)
     return eps

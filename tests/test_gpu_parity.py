@@ -2,6 +2,8 @@
 Oracle = tests/golden/*.pt, minted from the unmodified reference modules by oracle/make_golden.py
 (the reference ships no tests/golden vectors of its own).  Tolerances are BASELINE.json's:
 <=1e-4 max-abs in fp32 mode, <=2e-2 in bf16 mode; masks / composites / DDIM update bit-exact."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -51,6 +53,7 @@ FORWARD_CASES = [("dm1", "dm1_32", "dm1_checksum"), ("dm1", "dm1_64", "dm1_check
                           ("bf16", "sm100", "simt", True, TOL_BF16), ("bf16", "sm100", "sm100", False, TOL_BF16),
                           ("bf16", "sm100", "sm100", "no_upfuse", TOL_BF16),
                           ("bf16", "sm100", "sm100", "narrow", TOL_BF16),
+                          ("bf16", "sm100", "sm100", "pure_bf16", TOL_BF16),
                           ("bf16", "sm100", "sm100", True, TOL_BF16)])
 def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision, conv, attn, fuse, tol):
     g = golden("forwards.pt")
@@ -59,9 +62,11 @@ def test_unet_forward_matches_reference(pkg, golden, flavour, key, ck, precision
     want = g[ck] if ck else case["checksum"]
     assert abs(chk - want) <= 1e-6 * want, "seeded weights differ from the fixture"
     x, t = case["x"].cuda(), case["t"].cuda()
+    # variants: "narrow" = no int8 mantissa extension on pre-norm tensors; "pure_bf16" = every GEMM operand bf16
     eng = model.engine(x.shape[0], x.shape[2], x.shape[3], precision=precision, conv_impl=conv, attn_impl=attn,
                        fuse_gn_stats=bool(fuse), fuse_upsample=(fuse != "no_upfuse"),
-                       wide_prenorm=(0 if fuse == "narrow" else 2))
+                       wide_prenorm=(0 if fuse == "narrow" else 2),
+                       gemm_operands=("bf16" if fuse == "pure_bf16" else "fp16"))
     eps = eng.forward(x, t)
     torch.cuda.synchronize()
     err = (eps.cpu() - case["eps"]).abs().max().item()
@@ -284,62 +289,79 @@ def test_attack_loop_single_rank(pkg):
 
 
 def test_attack_decisions_agree_with_reference_sampler(pkg):
-    """North-star end-to-end criterion for the bf16 path: attack-success decisions of a victim on images
-    sampled by the bf16 CUDA path vs by the reference algorithm (oracle port, fp32, CPU) from the same
-    noise.  256 images, dm1 UNet, 32x32, DDIM-10, composite included.  The victim is a random-init linear
-    probe, so a few per cent of the images sit closer to a class boundary than ten bf16 UNet forwards can
-    resolve; the check is therefore: every image the reference decides by a clear margin (all but the closest
-    fifth) gets the same class and the same success flag, and over all images the flags agree on >= 98 %."""
+    """North-star end-to-end criterion: attack-success decisions on images sampled by the 16-bit CUDA path vs by the
+    reference algorithm from the same noise must agree on >= 99 % of the images -- all images, no margin carve-out.
+      * 1024 images, dm1 UNet, 32x32, free-running DDIM-10, dm2-flavour composite;
+      * victim: ResNet-50-shaped (torchvision resnet50, 37 classes, random init, eval) on Resize((224,224)) inputs
+        in [0,1] without normalisation (ASR_fast.py:90-97).  A random-init ResNet-50 predicts one class for every
+        input; its fc bias is re-centred on the clean images (bias -= mean clean logit) so decisions spread over
+        the classes.  "True" label = the victim's decision on the clean image; success = the shadow flips it;
+      * reference = oracle/torch_port.py (plain PyTorch fp32, TF32 off) run on the GPU for all 1024 images, itself
+        pinned here against the same oracle on the CPU for the first 32 (the CPU needs minutes for 1024)."""
+    import torchvision
     from oracle import torch_port as P
+    from advshadow_b200 import ops
+    from advshadow_b200.attack import victim_preprocess
+    from advshadow_b200.sampler import ShadowSampler
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     model, _ = get_model(pkg, "dm1")
     model.set_precision("bf16")
     gd = pkg["dm1"].GaussianDiffusion(timesteps=1000)
-    B, S, n = 256, 32, 10
+    N, chunk, S, n = 1024, 256, 32, 10
     g = torch.Generator().manual_seed(21)
-    x_T = torch.randn(B, 3, S, S, generator=g)
-    clean = torch.rand(B, 3, S, S, generator=g)
-    fmask = (torch.rand(B, 1, S, S, generator=g) > 0.3).float()
-    centers = torch.rand(B, 2, generator=g) * S
-    radii = torch.rand(B, generator=g) * 8 + 6
+    x_T = torch.randn(N, 3, S, S, generator=g)
+    clean = torch.rand(N, 3, S, S, generator=g)
+    fmask = (torch.rand(N, 1, S, S, generator=g) > 0.3).float()
+    centers = torch.rand(N, 2, generator=g) * S
+    radii = torch.rand(N, generator=g) * 8 + 6
     torch.manual_seed(3)
-    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, stride=2, padding=1), torch.nn.ReLU(), torch.nn.AvgPool2d(2),
-                                 torch.nn.Flatten(), torch.nn.Linear(16 * 8 * 8, 37)).eval()
-    with torch.no_grad():   # "true" label = the victim's decision on the clean image: success = the shadow flips it
-        labels = victim(clean).argmax(1)
-    # CUDA path
-    from advshadow_b200.sampler import ShadowSampler
-    from advshadow_b200 import ops
-    sampler = ShadowSampler(model, gd, B, S, ddim_timesteps=n)
-    out = sampler(x_T, clean, fmask, centers, radii)
+    victim = torchvision.models.resnet50(num_classes=37).eval().cuda()
+
+    @torch.no_grad()
+    def logits_of(imgs):
+        return torch.cat([victim(victim_preprocess(imgs[i:i + 128].cuda(), 224)).float() for i in range(0, len(imgs), 128)])
+
     with torch.no_grad():
-        logits_gpu = victim.cuda()(out.cuda()).float()
-    flags_gpu, counts = ops.success_flags(logits_gpu, labels.cuda())
-    # reference algorithm on the CPU
-    params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    with torch.no_grad():
-        x0 = P.ddim_sample(params, P.DM1_CFG, P.cosine_alphas_cumprod(), x_T, n)
-        ref_imgs = torch.stack([P.apply_shadow(clean[i], centers[i], radii[i], fmask[i], 0.33,
-                                               perturb=lambda s, i=i: x0[i].clamp(0, 1)[None])[0][0] for i in range(B)])
-        logits_ref = victim.cpu()(ref_imgs)
-        pred_ref = logits_ref.argmax(1)
-        flags_ref = pred_ref != labels
-    top2 = logits_ref.topk(2, dim=1).values
-    margin = top2[:, 0] - top2[:, 1]
-    clear = margin >= margin.quantile(0.2)
-    img_err = (out - ref_imgs).abs().max().item()
-    agree = (flags_gpu.cpu().bool() == flags_ref).float().mean().item()
-    pred_gpu = logits_gpu.argmax(1).cpu()
+        victim.fc.bias -= logits_of(clean).mean(0)
+    labels = logits_of(clean).argmax(1)
+    # ---- CUDA path ----
+    sampler = ShadowSampler(model, gd, chunk, S, ddim_timesteps=n)
+    out = torch.cat([sampler(x_T[i:i + chunk], clean[i:i + chunk], fmask[i:i + chunk], centers[i:i + chunk],
+                             radii[i:i + chunk]) for i in range(0, N, chunk)])
+    logits_gpu = logits_of(out)
+    flags_gpu, counts = ops.success_flags(logits_gpu, labels)
+    # ---- reference algorithm (fp32) ----
+    acp = P.cosine_alphas_cumprod()
+    params = {k: v.detach() for k, v in model.state_dict().items()}              # on the GPU
+
+    def reference_images(p, dev, lo, hi):
+        with torch.no_grad():
+            x0 = P.ddim_sample(p, P.DM1_CFG, acp, x_T[lo:hi].to(dev), n)
+            return torch.stack([P.apply_shadow(clean[i].to(dev), centers[i].to(dev), radii[i].to(dev), fmask[i].to(dev), 0.33,
+                                               perturb=lambda s_, j=i - lo: x0[j].clamp(0, 1)[None])[0][0]
+                                for i in range(lo, hi)])
+
+    ref_imgs = torch.cat([reference_images(params, "cuda", i, i + chunk) for i in range(0, N, chunk)]).cpu()
+    cpu_imgs = reference_images({k: v.cpu() for k, v in params.items()}, "cpu", 0, 32)
+    pin = (ref_imgs[:32] - cpu_imgs).abs().max().item()
+    logits_ref = logits_of(ref_imgs)
+    pred_ref, pred_gpu = logits_ref.argmax(1), logits_gpu.argmax(1)
+    flags_ref = pred_ref != labels
+    assert pin <= 2e-3 and torch.equal(logits_of(cpu_imgs).argmax(1), pred_ref[:32]), "oracle on GPU drifted from the oracle on CPU"
+    agree = (flags_gpu.bool() == flags_ref).float().mean().item()
     same_class = (pred_gpu == pred_ref).float().mean().item()
-    miss = (pred_gpu != pred_ref).nonzero().flatten()
-    print("reference margins of the images whose class differs:", [round(margin[i].item(), 4) for i in miss],
-          f"(median margin {margin.median().item():.4f}, 20th percentile {margin.quantile(0.2).item():.4f})")
-    print(f"bf16 DDIM-{n} + composite vs reference: max|image err| = {img_err:.3e}, decision agreement = {agree:.4f}, "
+    img_err = (out - ref_imgs).abs()
+    top2 = logits_ref.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1]).cpu()
+    miss = (pred_gpu != pred_ref).nonzero().flatten().cpu()
+    print(f"16-bit DDIM-{n} + composite vs reference, {N} images, ResNet-50-shaped victim at 224x224: decision agreement = {agree:.4f}, "
           f"same predicted class = {same_class:.4f}, successes {int(counts[0])}/{int(counts[1])} (reference {int(flags_ref.sum())}), "
-          f"{pred_ref.unique().numel()} distinct predicted classes")
-    assert pred_ref.unique().numel() >= 4 and 0 < int(flags_ref.sum()) < B, "degenerate victim: the check would be vacuous"
-    assert bool((pred_gpu[clear] == pred_ref[clear]).all()), "a clearly decided image changed class"
-    assert bool((flags_gpu.cpu().bool()[clear] == flags_ref[clear]).all()), "a clearly decided image changed its success flag"
-    assert agree >= 0.98 and same_class >= 0.97
+          f"{pred_ref.unique().numel()} distinct predicted classes; image err max {img_err.max():.3e} mean {img_err.mean():.3e}; "
+          f"oracle GPU-vs-CPU pin {pin:.2e}; reference margins of the images whose class differs: "
+          f"{[round(margin[i].item(), 4) for i in miss]} (median margin {margin.median().item():.4f})")
+    assert pred_ref.unique().numel() >= 8 and 0.05 * N < int(flags_ref.sum()) < 0.95 * N, "degenerate victim: the check would be vacuous"
+    assert agree >= 0.99 and same_class >= 0.99
     model.release_engines()
 
 
@@ -390,7 +412,7 @@ def test_ddim_sample_graph_reuse_across_calls(pkg):
     dict(model_channels=64, channel_mult=(1, 2), attention_resolutions=(2,), num_heads=2, num_res_blocks=1, H=32, W=48),
     dict(model_channels=32, channel_mult=(1, 2, 2), attention_resolutions=(1, 4), num_heads=4, num_res_blocks=2, H=24, W=24),
 ])
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_custom_unet_configs_vs_oracle_port(pkg, cfg, precision, tol):
     """Non-default UNet shapes (non-square input, channel counts that force the SIMT kernels in bf16 mode,
     attention at full resolution) against the CPU oracle port with the same seeded weights."""
@@ -453,7 +475,17 @@ def test_dm2_at_256_forward_and_teacher_forced_steps(pkg, golden):
     seq, prev = pkg["dm1"].ddim_timestep_tables(1000, d["n"], "uniform")
     coef = gd.ddim_coefficients(seq, prev, d["n"], 0.0).cuda()
     step = torch.zeros(1, dtype=torch.int32, device="cuda")
-    for precision, tol in (("bf16", TOL_BF16), ("fp32", TOL_FP32)):
+    for precision, tol in (("bf16", TOL_BF16), ("bf16-pure", None), ("fp32", TOL_FP32)):
+        if precision == "bf16-pure":
+            # informative: every GEMM operand bf16 (gemm_operands="bf16").  At this resolution the error has heavy
+            # tails (a few pixels with large activations), so single steps exceed 2e-2 -- why fp16 operands are the default
+            eng = model.engine(1, 256, 256, precision="bf16", gemm_operands="bf16")
+            for j, i in enumerate(d["steps"]):
+                x = (x_T if d["x"][j] is None else d["x"][j]).cuda()
+                err = (eng.forward(x, d["t"][j].cuda()).cpu() - d["eps"][j]).abs().max().item()
+                print(f"dm2 256x256 all-bf16 operands (informative): DDIM-50 step {i} max|eps err| = {err:.3e}")
+            model.release_engines()
+            continue
         eng = model.engine(1, 256, 256, precision=precision)
         if precision == "bf16":
             names = [n for (_, _, n) in eng._launches]

@@ -221,7 +221,7 @@ def test_capi_library_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.advs_version() >= 100
     import ctypes
-    assert ctypes.sizeof(_capi.ConvParams) == 200
+    assert ctypes.sizeof(_capi.ConvParams) == 208
 
 
 def test_no_cpu_fallback_and_error_surface(dm1_params):
