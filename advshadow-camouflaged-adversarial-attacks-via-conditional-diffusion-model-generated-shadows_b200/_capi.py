@@ -37,7 +37,7 @@ class ConvParams(C.Structure):
         ("stats_partial", C.c_void_p),
         ("up_phase", C.c_int32), ("stats_gran", C.c_int32),
         ("y_lo", C.c_void_p),
-        ("operand_f16", C.c_int32),
+        ("operand_f16", C.c_int32), ("qkv_dh_pad", C.c_int32),
     ]
 
 
@@ -75,6 +75,7 @@ SIGNATURES = {
     "advs_attention_simt_workspace_bytes": (_sz, [_i, _i, _i]),
     "advs_attention_simt": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "advs_attention_sm100_plan": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "advs_attention_sm100_plan_ex": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "advs_attention_sm100_launch": (C.c_int, [_vp, _vp]),
     "advs_ddim_step": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _vp]),
     "advs_ddpm_step": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _i, _i, _vp]),
@@ -91,6 +92,9 @@ SIGNATURES = {
     "advs_copy_channels": (C.c_int, [_vp, _vp, _sz, _i, _i, _i, _i, _vp]),
     "advs_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _i, _f, _i, _vp]),
     "advs_groupnorm_apply_ex": (C.c_int, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp]),
+    "advs_groupnorm_apply_ex16": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp]),
+    "advs_layernorm_f16out": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _i, _f, _vp]),
+    "advs_pos_encoding_ex": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "advs_activation": (C.c_int, [_vp, _vp, _sz, _i, _i, _vp]),
     "advs_pos_encoding": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "advs_cfg_lerp": (C.c_int, [_vp, _vp, _f, _vp, _sz, _vp]),

@@ -23,6 +23,11 @@
 // MMA from there, so PV only streams V from shared memory.  dh = 256 fills TMEM with S and O; its P goes
 // through one swizzled shared-memory tile.
 // q and k arrive pre-scaled by dh^-1/4 each (dm1:121-122), so the softmax scale is 1.
+// T need not be a multiple of 128: the last key block is partial.  Its out-of-range score columns are set to -inf
+// before the row maximum (they hold the next head's keys, or TMA zero fill past the end of the tensor), the V^T box
+// is zero-filled by TMA past column T (so 0 * garbage never occurs), and query rows past T are computed but not
+// stored.  Head dims below 64 (IDDM: 16 and 32) run as dh = 64 with zero-padded q / k / v^T; only the first
+// dh_valid output columns of each head are stored, packed.
 #include <string.h>
 
 #include "common.cuh"
@@ -38,6 +43,7 @@ struct AttnMaps {
 
 struct AttnArgs {
   int B, heads, T, dh;
+  int dh_valid;   // head dim of the problem; q / k / v^T are zero-padded to dh (= the kernel's DH) when smaller
   __nv_bfloat16* o;
 };
 
@@ -120,7 +126,8 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tile = blockIdx.x;
   const int bh = blockIdx.y;
-  const int nblk = a.T / kBK;
+  const int nblk = (a.T + kBK - 1) / kBK;
+  const int tail = a.T - (nblk - 1) * kBK;       // valid keys in the last block (kBK when T is a multiple of it)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -265,6 +272,11 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[set]);      // S_{j+2} may overwrite the buffer
+      if (j == nblk - 1 && tail < kBK) {             // partial last key block (warp-uniform branch)
+#pragma unroll
+        for (int i = 0; i < kBK; ++i)
+          if (i >= tail) s[i] = -INFINITY;
+      }
       if (warp == kAttnFirstSoftmaxWarp) TR(1);
       float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
 #pragma unroll
@@ -359,15 +371,19 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
     const float inv = 1.f / l;
     constexpr int HD = DH / 2;    // O columns per warp: the two sets split the columns of their 32 rows
     const int b = bh / a.heads, head = bh - b * a.heads;
-    __nv_bfloat16* orow = a.o + ((size_t)b * a.T + q_tile * kBQ + row) * ((size_t)a.heads * DH) + (size_t)head * DH + set * HD;
+    const int dv = a.dh_valid;
+    const bool row_ok = q_tile * kBQ + row < a.T;
+    __nv_bfloat16* orow = a.o + ((size_t)b * a.T + q_tile * kBQ + row) * ((size_t)a.heads * dv) + (size_t)head * dv + set * HD;
 #pragma unroll 1
     for (int c = 0; c < HD / 32; ++c) {
+      if (set * HD + c * 32 >= dv) break;            // padded head dim: nothing to store (warp-uniform)
       uint32_t r[32];
       tmem_ld_32x32b_x32(lane_addr + Cfg::o_col + set * HD + c * 32, r);
       tmem_wait_ld();
       uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
+        if (row_ok && set * HD + c * 32 + 8 * i < dv)
         dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i + 0]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
                             pack_bf16x2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
                             pack_bf16x2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
@@ -392,7 +408,7 @@ static int attn_launch(const AttnPlan* plan, cudaStream_t st) {
       return ADVS_ERR_CUDA;
     }
   }
-  dim3 grid(plan->args.T / kBQ, plan->args.B * plan->args.heads);
+  dim3 grid((plan->args.T + kBQ - 1) / kBQ, plan->args.B * plan->args.heads);
   k_attention_sm100<DH><<<grid, kAttnThreads, AttnCfg<DH>::smem_bytes, st>>>(plan->maps, plan->args);
   ADVS_CHECK_LAUNCH("attention_sm100_launch");
   return ADVS_OK;
@@ -410,12 +426,16 @@ extern "C" int advs_debug_attn_trace(long long* host_out) {
 
 extern "C" {
 
-int advs_attention_sm100_plan(const void* q, const void* k, const void* vt, void* o, int B, int heads, int T, int dh,
-                              void* plan_host) {
+int advs_attention_sm100_plan_ex(const void* q, const void* k, const void* vt, void* o, int B, int heads, int T, int dh,
+                                 int dh_valid, void* plan_host) {
   ADVS_CHECK_ARG(q && k && vt && o && plan_host, "attention_sm100_plan: null pointer");
   ADVS_CHECK_ARG(((uintptr_t)plan_host % 64) == 0, "attention_sm100_plan: plan buffer must be 64-byte aligned");
-  ADVS_CHECK_ARG(B > 0 && heads > 0 && T > 0 && T % 128 == 0, "attention_sm100_plan: T must be a positive multiple of 128");
+  ADVS_CHECK_ARG(B > 0 && heads > 0 && T > 0 && T % 8 == 0,
+                 "attention_sm100_plan: T must be a positive multiple of 8 (TMA row pitch of v^T: 16 bytes)");
   ADVS_CHECK_ARG(dh == 64 || dh == 128 || dh == 256, "attention_sm100_plan: dh must be 64, 128 or 256");
+  ADVS_CHECK_ARG(dh_valid > 0 && dh_valid <= dh && dh_valid % 8 == 0 && (dh_valid == dh || dh == 64),
+                 "attention_sm100_plan: dh_valid must be a multiple of 8, <= dh, and < dh only with dh = 64");
+  ADVS_CHECK_ARG(((uintptr_t)o % 16) == 0 && (heads * dh_valid) % 8 == 0, "attention_sm100_plan: output rows must be 16-byte aligned");
   ADVS_CHECK_ARG((long long)B * heads <= 65535, "attention_sm100_plan: B*heads must be <= 65535");
   AttnPlan* plan = reinterpret_cast<AttnPlan*>(plan_host);
   memset(plan, 0, sizeof(AttnPlan));
@@ -440,9 +460,15 @@ int advs_attention_sm100_plan(const void* q, const void* k, const void* vt, void
   plan->args.heads = heads;
   plan->args.T = T;
   plan->args.dh = dh;
+  plan->args.dh_valid = dh_valid;
   plan->args.o = reinterpret_cast<__nv_bfloat16*>(o);
   plan->magic = 0xA77EB200u;
   return ADVS_OK;
+}
+
+int advs_attention_sm100_plan(const void* q, const void* k, const void* vt, void* o, int B, int heads, int T, int dh,
+                              void* plan_host) {
+  return advs_attention_sm100_plan_ex(q, k, vt, o, B, heads, T, dh, dh, plan_host);
 }
 
 int advs_attention_sm100_launch(const void* plan_host, void* stream) {

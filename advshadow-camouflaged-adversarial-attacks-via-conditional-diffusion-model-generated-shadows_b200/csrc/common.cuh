@@ -128,6 +128,7 @@ struct EpilogueParams {
   void* vt;
   int heads;
   int dh;
+  int dh_pad;      // storage head dim of q / k / vt (>= dh)
   float qk_scale;
   int HW;    // pixels per image (T for attention)
   int Cout;
@@ -148,6 +149,7 @@ inline EpilogueParams make_epilogue(const advs_conv_params& p) {
   e.vt = p.vt;
   e.heads = p.heads > 0 ? p.heads : 1;
   e.dh = p.out_mode == 1 ? p.Cout / (3 * e.heads) : 0;
+  e.dh_pad = p.qkv_dh_pad > e.dh ? p.qkv_dh_pad : e.dh;
   e.qk_scale = p.qk_scale;
   e.HW = p.H * p.W;
   e.Cout = p.Cout;

@@ -281,7 +281,9 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
     ADVS_CHECK_ARG(p->seg[s].C % 64 == 0, "conv_sm100_plan: segment channels must be multiples of 64");
   if (p->out_mode == 1) {
     int dh = p->Cout / (3 * p->heads);
-    ADVS_CHECK_ARG(dh % 32 == 0, "conv_sm100_plan: head dim must be a multiple of 32");
+    ADVS_CHECK_ARG(dh % 32 == 0 || dh == 16, "conv_sm100_plan: head dim must be 16 or a multiple of 32");
+    ADVS_CHECK_ARG(p->qkv_dh_pad == 0 || (p->qkv_dh_pad >= dh && p->qkv_dh_pad % 8 == 0),
+                   "conv_sm100_plan: qkv_dh_pad must be a multiple of 8 and >= the head dim");
   }
   ADVS_CHECK_ARG(!p->bias || ((uintptr_t)p->bias % 16) == 0, "conv_sm100_plan: bias must be 16-byte aligned");
   ADVS_CHECK_ARG(!p->temb || (((uintptr_t)p->temb % 16) == 0 && p->temb_stride % 4 == 0),

@@ -129,27 +129,39 @@ __device__ __forceinline__ void epilogue_write32(const EpilogueParams& e, const 
     for (int j = 0; j < 32; ++j)
       if (n + j < e.cout_valid) dst[(size_t)j * e.HW] = v[j];
   } else {
-    const int head = n / (3 * e.dh);
-    const int r = n - head * 3 * e.dh;
-    const int which = r / e.dh;
-    const int d0 = r - which * e.dh;
-    const size_t bh = (size_t)b * e.heads + head;
-    if (which < 2) {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh + d0;
-      uint4* yp = reinterpret_cast<uint4*>(dst);
+    // 32 consecutive output channels = one piece of a head's [q | k | v] block, or two 16-wide pieces when dh = 16
+    const int g = e.dh >= 32 ? 32 : 16;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16x2(v[8 * j] * e.qk_scale, v[8 * j + 1] * e.qk_scale);
-        o.y = pack_bf16x2(v[8 * j + 2] * e.qk_scale, v[8 * j + 3] * e.qk_scale);
-        o.z = pack_bf16x2(v[8 * j + 4] * e.qk_scale, v[8 * j + 5] * e.qk_scale);
-        o.w = pack_bf16x2(v[8 * j + 6] * e.qk_scale, v[8 * j + 7] * e.qk_scale);
-        yp[j] = o;
+    for (int sub = 0; sub < 2; ++sub) {
+      if (sub * g >= 32) break;
+      const int nn = n + sub * g;
+      const int head = nn / (3 * e.dh);
+      const int r = nn - head * 3 * e.dh;
+      const int which = r / e.dh;
+      const int d0 = r - which * e.dh;
+      const size_t bh = (size_t)b * e.heads + head;
+      const float* vv = v + sub * g;
+      if (which < 2) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh_pad + d0;
+        uint4* yp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (8 * j >= g) break;
+          uint4 o;
+          o.x = pack_bf16x2(vv[8 * j] * e.qk_scale, vv[8 * j + 1] * e.qk_scale);
+          o.y = pack_bf16x2(vv[8 * j + 2] * e.qk_scale, vv[8 * j + 3] * e.qk_scale);
+          o.z = pack_bf16x2(vv[8 * j + 4] * e.qk_scale, vv[8 * j + 5] * e.qk_scale);
+          o.w = pack_bf16x2(vv[8 * j + 6] * e.qk_scale, vv[8 * j + 7] * e.qk_scale);
+          yp[j] = o;
+        }
+      } else {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh_pad + d0) * e.HW + t;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j >= g) break;
+          dst[(size_t)j * e.HW] = __float2bfloat16_rn(vv[j]);
+        }
       }
-    } else {
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh + d0) * e.HW + t;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) dst[(size_t)j * e.HW] = __float2bfloat16_rn(v[j]);
     }
   }
 }

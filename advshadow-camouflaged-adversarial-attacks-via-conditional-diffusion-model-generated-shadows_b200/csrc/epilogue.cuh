@@ -28,9 +28,9 @@ __device__ __forceinline__ void epilogue_store1(const EpilogueParams& e, size_t 
     int which = r / e.dh;
     int d = r - which * e.dh;
     size_t bh = (size_t)b * e.heads + head;
-    if (which == 0) reinterpret_cast<T*>(e.q)[(bh * e.HW + t) * e.dh + d] = from_f<T>(v * e.qk_scale);
-    else if (which == 1) reinterpret_cast<T*>(e.k)[(bh * e.HW + t) * e.dh + d] = from_f<T>(v * e.qk_scale);
-    else reinterpret_cast<T*>(e.vt)[(bh * e.dh + d) * e.HW + t] = from_f<T>(v);
+    if (which == 0) reinterpret_cast<T*>(e.q)[(bh * e.HW + t) * e.dh_pad + d] = from_f<T>(v * e.qk_scale);
+    else if (which == 1) reinterpret_cast<T*>(e.k)[(bh * e.HW + t) * e.dh_pad + d] = from_f<T>(v * e.qk_scale);
+    else reinterpret_cast<T*>(e.vt)[(bh * e.dh_pad + d) * e.HW + t] = from_f<T>(v);
   }
 }
 

@@ -94,7 +94,7 @@ __global__ void k_copy_channels(const T* __restrict__ x, T* __restrict__ y, size
 }
 
 // ---- nn.LayerNorm([C]) over the channel axis of each token (attention.py:29,31); one warp per token ----
-template <typename T>
+template <typename T, bool OUT_F16 = false>
 __global__ void k_layernorm(const T* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
                             T* __restrict__ y, size_t rows, int C, float eps) {
   size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -113,15 +113,19 @@ __global__ void k_layernorm(const T* __restrict__ x, const float* __restrict__ g
   q = warp_sum(q);
   const float rstd = rsqrtf(q / C + eps);
   T* yr = y + row * C;
-  for (int c = lane; c < C; c += 32) yr[c] = from_f<T>((to_f(xr[c]) - mean) * rstd * g[c] + bta[c]);
+  for (int c = lane; c < C; c += 32) {
+    const float v = (to_f(xr[c]) - mean) * rstd * g[c] + bta[c];
+    if constexpr (OUT_F16 && sizeof(T) == 2) reinterpret_cast<__half*>(yr)[c] = __float2half_rn(v);   // bounded: fp16 GEMM operand
+    else yr[c] = from_f<T>(v);
+  }
 }
 
 // ---- GroupNorm apply with the DoubleConv / Down/UpBlock epilogues folded in:
 //      y = act( x*scale + shift (+ residual) ) (+ emb[b, c])     (conv.py:40-66, block.py:44-46) ----
-template <typename T>
+template <typename T, bool OUT_F16 = false>
 __global__ void k_gn_apply_ex(const T* __restrict__ x, int HW, int C, size_t npix, const float* __restrict__ scale_shift,
                               const T* __restrict__ residual, const float* __restrict__ emb, int emb_stride, int act,
-                              T* __restrict__ y) {
+                              T* __restrict__ y, const uint8_t* __restrict__ x_lo = nullptr) {
   const int cv = C / 8;
   size_t total = npix * cv;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -133,7 +137,12 @@ __global__ void k_gn_apply_ex(const T* __restrict__ x, int HW, int C, size_t npi
     Vec8<T> v;
     v.load(x + p * C + c);
     float f[8], r[8];
-    v.to_float(f);
+    if constexpr (sizeof(T) == 2) {
+      if (x_lo) wide_decode8(v.v, *reinterpret_cast<const uint2*>(x_lo + p * C + c), f);   // bf16 + int8 extension
+      else v.to_float(f);
+    } else {
+      v.to_float(f);
+    }
     if (residual) {
       Vec8<T> rv;
       rv.load(residual + p * C + c);
@@ -148,7 +157,13 @@ __global__ void k_gn_apply_ex(const T* __restrict__ x, int HW, int C, size_t npi
       if (emb) a += emb[(size_t)b * emb_stride + c + i];
       f[i] = a;
     }
-    v.from_float(f);
+    if constexpr (OUT_F16 && sizeof(T) == 2) {
+      __half2* h = reinterpret_cast<__half2*>(&v.v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    } else {
+      v.from_float(f);
+    }
     v.store(y + p * C + c);
   }
 }
@@ -170,13 +185,13 @@ __global__ void k_act(const T* __restrict__ x, T* __restrict__ y, size_t n, int 
 // ---- BaseNet.pos_encoding (base.py:56-68): [sin(t f_j) | cos(t f_j)], then time += label_emb(y) (unet.py:106-107) ----
 __global__ void k_pos_encoding(const int64_t* __restrict__ t, const float* __restrict__ inv_freq, int half,
                                const int64_t* __restrict__ labels, const float* __restrict__ label_emb, int nt,
-                               float* __restrict__ out) {
+                               float* __restrict__ out, int n_labeled) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nt * half) return;
   int r = i / half, j = i % half;
   float a = __fmul_rn((float)t[r], inv_freq[j]);
   float s = sinf(a), c = cosf(a);
-  if (labels) {
+  if (labels && r < n_labeled) {
     const float* e = label_emb + (size_t)labels[r] * 2 * half;
     s = __fadd_rn(s, e[j]);
     c = __fadd_rn(c, e[half + j]);
@@ -254,6 +269,15 @@ int advs_copy_channels(const void* x, void* y, size_t npix, int C, int y_cstride
   return ADVS_OK;
 }
 
+int advs_layernorm_f16out(const void* x, const float* gamma, const float* beta, void* y, size_t rows, int C, float eps,
+                          void* stream) {
+  ADVS_CHECK_ARG(x && y && gamma && beta && rows > 0 && C > 0, "layernorm: bad args");
+  k_layernorm<__nv_bfloat16, true><<<blocks_for(rows * 32), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)y, rows, C, eps);
+  ADVS_CHECK_LAUNCH("layernorm_f16out");
+  return ADVS_OK;
+}
+
 int advs_layernorm(const void* x, const float* gamma, const float* beta, void* y, size_t rows, int C, float eps, int dtype,
                    void* stream) {
   ADVS_CHECK_ARG(x && y && gamma && beta && rows > 0 && C > 0, "layernorm: bad args");
@@ -282,6 +306,28 @@ int advs_groupnorm_apply_ex(const void* x, int B, int HW, int C, const float* sc
   return ADVS_OK;
 }
 
+int advs_groupnorm_apply_ex16(const void* x, const void* x_lo, int B, int HW, int C, const float* scale_shift,
+                              const void* residual, const float* emb, int emb_stride, int act, void* y, int y_dtype,
+                              void* stream) {
+  ADVS_CHECK_ARG(x && y && scale_shift && B > 0 && HW > 0 && C % 8 == 0 && act >= 0 && act <= 2, "groupnorm_apply_ex16: bad args");
+  ADVS_CHECK_ARG(y_dtype == ADVS_BF16 || y_dtype == ADVS_F16, "groupnorm_apply_ex16: y_dtype must be ADVS_BF16 or ADVS_F16");
+  ADVS_CHECK_ARG(((uintptr_t)x_lo % 8) == 0, "groupnorm_apply_ex16: x_lo must be 8-byte aligned");
+  size_t npix = (size_t)B * HW;
+  size_t total = npix * (C / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  using T = __nv_bfloat16;
+  if (y_dtype == ADVS_F16)
+    k_gn_apply_ex<T, true><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, HW, C, npix, scale_shift, (const T*)residual, emb,
+                                                             emb_stride, act, (T*)y, (const uint8_t*)x_lo);
+  else
+    k_gn_apply_ex<T, false><<<(unsigned)blocks, 256, 0, st>>>((const T*)x, HW, C, npix, scale_shift, (const T*)residual, emb,
+                                                              emb_stride, act, (T*)y, (const uint8_t*)x_lo);
+  ADVS_CHECK_LAUNCH("groupnorm_apply_ex16");
+  return ADVS_OK;
+}
+
 int advs_activation(const void* x, void* y, size_t n, int act, int dtype, void* stream) {
   ADVS_CHECK_ARG(x && y && n > 0 && n % 8 == 0 && act >= 0 && act <= 2, "activation: bad args (n%%8)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -292,12 +338,18 @@ int advs_activation(const void* x, void* y, size_t n, int act, int dtype, void* 
   return ADVS_OK;
 }
 
-int advs_pos_encoding(const int64_t* t, int nt, const float* inv_freq, int half, const int64_t* labels,
-                      const float* label_emb, float* out, void* stream) {
-  ADVS_CHECK_ARG(t && inv_freq && out && nt > 0 && half > 0 && (!labels || label_emb), "pos_encoding: bad args");
-  k_pos_encoding<<<blocks_for((size_t)nt * half, 128), 128, 0, (cudaStream_t)stream>>>(t, inv_freq, half, labels, label_emb, nt, out);
+int advs_pos_encoding_ex(const int64_t* t, int nt, const float* inv_freq, int half, const int64_t* labels,
+                         const float* label_emb, int n_labeled, float* out, void* stream) {
+  ADVS_CHECK_ARG(t && inv_freq && out && nt > 0 && half > 0 && (!labels || label_emb) && n_labeled >= 0, "pos_encoding: bad args");
+  k_pos_encoding<<<blocks_for((size_t)nt * half, 128), 128, 0, (cudaStream_t)stream>>>(t, inv_freq, half, labels, label_emb, nt, out,
+                                                                                      n_labeled);
   ADVS_CHECK_LAUNCH("pos_encoding");
   return ADVS_OK;
+}
+
+int advs_pos_encoding(const int64_t* t, int nt, const float* inv_freq, int half, const int64_t* labels,
+                      const float* label_emb, float* out, void* stream) {
+  return advs_pos_encoding_ex(t, nt, inv_freq, half, labels, label_emb, nt, out, stream);
 }
 
 int advs_cfg_lerp(const float* uncond, const float* cond, float w, float* out, size_t n, void* stream) {

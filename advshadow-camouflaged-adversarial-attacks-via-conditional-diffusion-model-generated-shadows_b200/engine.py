@@ -162,7 +162,8 @@ class UNetEngine:
 
     # ---- helpers ----
     def _attn_sm100_ok(self, a):
-        return self.attn_impl == "sm100" and a["T"] % 128 == 0 and a["dh"] in (64, 128, 256)
+        # (a partial last key block is masked in-kernel; T % 8: TMA row pitch of v^T)
+        return self.attn_impl == "sm100" and a["T"] % 8 == 0 and a["dh"] in (64, 128, 256)
 
     def _conv_sm100_ok(self, a):
         if self.conv_impl != "sm100":

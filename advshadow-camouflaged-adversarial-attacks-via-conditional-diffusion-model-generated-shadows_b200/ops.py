@@ -74,8 +74,9 @@ def groupnorm(x0, x1, gamma, beta, groups=32, eps=1e-5, silu=False):
     return y
 
 
-def conv(segs, B, H, W, cout, stride=1, bias=None, temb=None, residual=None, qkv_heads=None, impl="simt"):
-    """segs: list of (x NHWC, packed weight [Cout][taps][C]).  Returns y NHWC, or (q, k, vt)."""
+def conv(segs, B, H, W, cout, stride=1, bias=None, temb=None, residual=None, qkv_heads=None, impl="simt", qkv_dh_pad=0):
+    """segs: list of (x NHWC, packed weight [Cout][taps][C]).  Returns y NHWC, or (q, k, vt) (zero-padded to
+    `qkv_dh_pad` columns / rows per head when that is larger than the head dim)."""
     x0 = segs[0][0]
     _need_cuda(x0)
     dev, dtype = x0.device, x0.dtype
@@ -92,10 +93,11 @@ def conv(segs, B, H, W, cout, stride=1, bias=None, temb=None, residual=None, qkv
     if qkv_heads:
         dh = cout // (3 * qkv_heads)
         T = H * W
-        q = torch.empty(B, qkv_heads, T, dh, dtype=dtype, device=dev)
-        k = torch.empty(B, qkv_heads, T, dh, dtype=dtype, device=dev)
-        vt = torch.empty(B, qkv_heads, dh, T, dtype=dtype, device=dev)
-        cp.out_mode, cp.q, cp.k, cp.vt, cp.heads = 1, _p(q), _p(k), _p(vt), qkv_heads
+        dhs = max(dh, qkv_dh_pad)
+        q = torch.zeros(B, qkv_heads, T, dhs, dtype=dtype, device=dev)
+        k = torch.zeros(B, qkv_heads, T, dhs, dtype=dtype, device=dev)
+        vt = torch.zeros(B, qkv_heads, dhs, T, dtype=dtype, device=dev)
+        cp.out_mode, cp.q, cp.k, cp.vt, cp.heads, cp.qkv_dh_pad = 1, _p(q), _p(k), _p(vt), qkv_heads, qkv_dh_pad
         cp.qk_scale = 1.0 / math.sqrt(math.sqrt(dh))
         ret = (q, k, vt)
     else:
@@ -114,10 +116,11 @@ def conv(segs, B, H, W, cout, stride=1, bias=None, temb=None, residual=None, qkv
     return ret
 
 
-def attention(q, k, vt, impl="simt"):
+def attention(q, k, vt, impl="simt", dh_valid=None):
+    """`dh_valid` (sm100 only): q / k / vt are zero-padded from that head dim to dh = 64; the output is packed."""
     _need_cuda(q, k, vt)
     B, heads, T, dh = q.shape
-    o = torch.empty(B, T, heads * dh, dtype=q.dtype, device=q.device)
+    o = torch.empty(B, T, heads * (dh_valid or dh), dtype=q.dtype, device=q.device)
     with torch.cuda.device(q.device):
         if impl == "simt":
             wsb = int(capi.lib().advs_attention_simt_workspace_bytes(B, heads, T))
@@ -125,7 +128,7 @@ def attention(q, k, vt, impl="simt"):
             capi.call("advs_attention_simt", _p(q), _p(k), _p(vt), _p(o), B, heads, T, dh, _p(ws), wsb, _dt(q), _st())
         elif impl == "sm100":
             pb = capi.PlanBuffer(capi.ATTN_PLAN_BYTES)
-            capi.call("advs_attention_sm100_plan", _p(q), _p(k), _p(vt), _p(o), B, heads, T, dh, pb.ptr)
+            capi.call("advs_attention_sm100_plan_ex", _p(q), _p(k), _p(vt), _p(o), B, heads, T, dh, dh_valid or dh, pb.ptr)
             capi.call("advs_attention_sm100_launch", pb.ptr, _st())
         else:
             raise ValueError(impl)

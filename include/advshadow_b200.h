@@ -185,6 +185,10 @@ typedef struct advs_conv_params {
    * (a GroupNorm output written by advs_groupnorm_apply_wide with y_dtype = ADVS_F16), bit 1 = the activations of
    * segments 1..2, bit 2 = the packed weights of segment 0, bit 3 = the packed weights of segments 1..2. */
   int32_t operand_f16;
+  /* out_mode 1: storage head dim of q / k / vt when it is larger than dh = Cout / (3*heads) (0 = dh): the epilogue
+   * writes the dh real columns of each head into rows of qkv_dh_pad elements (q, k) / into the first dh of
+   * qkv_dh_pad rows (vt); the caller zero-fills the buffers once.  See advs_attention_sm100_plan_ex. */
+  int32_t qkv_dh_pad;
 } advs_conv_params;
 
 /* generic SIMT fp32-accumulate implementation: any dtype, any channel counts (multiple of 4) */
@@ -215,10 +219,15 @@ int advs_attention_simt(const void* q, const void* k, const void* vt, void* o, i
                         int T, int dh, void* workspace, size_t workspace_bytes, int dtype,
                         void* stream);
 /* sm_100a flash-attention (tcgen05 QK^T and PV, online softmax in fp32), bf16, dh in {64,128,256},
- * T multiple of 128. */
+ * T a multiple of 8 (a partial last key block is masked in-kernel).
+ * _plan_ex: head dims below 64 (IDDM's nn.MultiheadAttention with 4 heads: 16 and 32, model/modules/attention.py:27)
+ * run with dh = 64 storage -- q, k [B,heads,T,64] and vt [B,heads,64,T] zero beyond dh_valid (advs_conv_params.
+ * qkv_dh_pad makes the qkv epilogue write them so) -- and o [B,T,heads*dh_valid] packed. */
 #define ADVS_ATTN_PLAN_BYTES 1024
 int advs_attention_sm100_plan(const void* q, const void* k, const void* vt, void* o, int B,
                               int heads, int T, int dh, void* plan_host);
+int advs_attention_sm100_plan_ex(const void* q, const void* k, const void* vt, void* o, int B,
+                                 int heads, int T, int dh, int dh_valid, void* plan_host);
 int advs_attention_sm100_launch(const void* plan_host, void* stream);
 
 /* ---- K8: DDIM / DDPM reverse-step updates (dm1:449-472, dm1:356-395) ---------------------- */
@@ -290,11 +299,22 @@ int advs_layernorm(const void* x, const float* gamma, const float* beta, void* y
  * + activation + residual form (conv.py:40-66) and the "x + emb" of Down/UpBlock (block.py:44-46, 76-78) */
 int advs_groupnorm_apply_ex(const void* x, int B, int HW, int C, const float* scale_shift, const void* residual,
                             const float* emb, int emb_stride, int act, void* y, int dtype, void* stream);
+/* 16-bit mode variants: x may carry an int8 mantissa extension x_lo (advs_conv_params.y_lo; NULL = none); y_dtype =
+ * ADVS_F16 writes a (bounded) normalised tensor as an fp16 GEMM operand.  advs_layernorm_f16out: bf16 in, fp16 out. */
+int advs_groupnorm_apply_ex16(const void* x, const void* x_lo, int B, int HW, int C, const float* scale_shift,
+                              const void* residual, const float* emb, int emb_stride, int act, void* y, int y_dtype,
+                              void* stream);
+int advs_layernorm_f16out(const void* x, const float* gamma, const float* beta, void* y, size_t rows, int C, float eps,
+                          void* stream);
 int advs_activation(const void* x, void* y, size_t n, int act, int dtype, void* stream);
 /* BaseNet.pos_encoding: out[i] = [sin(t_i f_j) | cos(t_i f_j)] (+ label_emb[labels[i]] when labels != NULL);
  * inv_freq[half] is the reference's 1/10000^(arange(0,C,2)/C) table (base.py:63), evaluated by the host */
 int advs_pos_encoding(const int64_t* t, int nt, const float* inv_freq, int half, const int64_t* labels,
                       const float* label_emb, float* out, void* stream);
+/* same; only rows [0, n_labeled) get the label embedding: the conditional and the unconditional prediction of
+ * classifier-free guidance (ddim.py:81-85) as ONE forward over 2n rows */
+int advs_pos_encoding_ex(const int64_t* t, int nt, const float* inv_freq, int half, const int64_t* labels,
+                         const float* label_emb, int n_labeled, float* out, void* stream);
 /* torch.lerp(uncond, cond, w): classifier-free guidance (ddim.py:89) */
 int advs_cfg_lerp(const float* uncond, const float* cond, float w, float* out, size_t n, void* stream);
 /* ((x + 1) * 0.5 * 255).type(uint8) without clamp (ddim.py:97-99) */

@@ -375,7 +375,54 @@ def schedules():
     return out
 
 
-MINTERS = dict(config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+def iddm_ckpt_cases():
+    """utils/checkpoint.py (save_ckpt / load_model_ckpt / load_ckpt, :21-157) run on a toy module: the dict the
+    reference writes, and the state_dict its loader produces for every (is_train, is_pretrain, is_distributed) mode
+    from checkpoints with and without the DistributedDataParallel `module.` prefix."""
+    import tempfile
+    R.install_stubs()
+    if R.REF_ROOT not in sys.path:
+        sys.path.insert(0, R.REF_ROOT)
+    from utils import checkpoint as ck
+
+    def toy(classes=5, prefix=False):
+        torch.manual_seed(classes)
+        m = torch.nn.Module()
+        m.label_emb = torch.nn.Embedding(classes, 8)
+        m.inc = torch.nn.Conv2d(3, 4, 3)
+        if prefix:
+            w = torch.nn.Module()
+            w.module = m
+            return w
+        return m
+
+    out = {"cases": []}
+    with tempfile.TemporaryDirectory() as d:
+        src = toy(5)
+        opt = torch.optim.SGD(src.parameters(), lr=0.1, momentum=0.9)
+        ck.save_ckpt(epoch=7, save_name="ckpt_7", ckpt_model=src.state_dict(), ckpt_ema_model=None,
+                     ckpt_optimizer=opt.state_dict(), results_dir=d, save_model_interval=True, start_model_interval=3,
+                     num_classes=5, conditional=True, image_size=64, sample="ddim", network="unet", act="gelu",
+                     classes_name=["a", "b"])
+        out["files"] = sorted(os.listdir(d))
+        out["saved"] = torch.load(os.path.join(d, "ckpt_last.pt"), weights_only=False)
+        for ckpt_prefix in (False, True):
+            ckpt_sd = toy(5, ckpt_prefix).state_dict()
+            for (is_train, is_pretrain, is_dist) in ((False, False, False), (True, True, False), (True, True, True), (True, False, False)):
+                for classes in (5, 9):                       # 9: the label embedding has another shape and is filtered out
+                    want_prefix = is_train and ((is_pretrain and is_dist) or (not is_pretrain and ckpt_prefix))
+                    model = toy(classes, want_prefix)
+                    try:
+                        ck.load_model_ckpt(model, dict(ckpt_sd), is_train=is_train, is_pretrain=is_pretrain, is_distributed=is_dist)
+                        res = {k: v.clone() for k, v in model.state_dict().items()}
+                    except Exception as e:                     # e.g. KeyError when the prefixes cannot be reconciled
+                        res = type(e).__name__
+                    out["cases"].append(dict(ckpt_prefix=ckpt_prefix, is_train=is_train, is_pretrain=is_pretrain,
+                                             is_distributed=is_dist, classes=classes, model_prefix=want_prefix, result=res))
+    return out
+
+
+MINTERS = dict(iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

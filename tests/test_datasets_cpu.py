@@ -38,3 +38,58 @@ def test_image_mask_label_formats(tmp_path):
     out = tmp_path / "shadowed_images"
     D.save_images(torch.rand(3, 3, 8, 8), str(out), names)
     assert sorted(os.listdir(out)) == sorted(names)
+
+
+def test_iddm_checkpoint_dict_matches_reference(golden, tmp_path):
+    """the IDDM on-disk checkpoint (utils/checkpoint.py:21-157).  Golden = what the reference's own
+    save_ckpt wrote and what its load_model_ckpt produced for every mode, with and without the DDP `module.` prefix."""
+    import torch
+    import advshadow_b200
+    from advshadow_b200 import iddm
+    g = golden("iddm_ckpt.pt")
+
+    def toy(classes=5, prefix=False):
+        torch.manual_seed(classes)
+        m = torch.nn.Module()
+        m.label_emb = torch.nn.Embedding(classes, 8)
+        m.inc = torch.nn.Conv2d(3, 4, 3)
+        if prefix:
+            w = torch.nn.Module()
+            w.module = m
+            return w
+        return m
+
+    src = toy(5)
+    opt = torch.optim.SGD(src.parameters(), lr=0.1, momentum=0.9)
+    iddm.save_ckpt(epoch=7, save_name="ckpt_7", ckpt_model=src.state_dict(), ckpt_ema_model=None,
+                   ckpt_optimizer=opt.state_dict(), results_dir=str(tmp_path), save_model_interval=True, start_model_interval=3,
+                   num_classes=5, conditional=True, image_size=64, sample="ddim", network="unet", act="gelu",
+                   classes_name=["a", "b"])
+    import os
+    assert sorted(os.listdir(tmp_path)) == g["files"]
+    mine = torch.load(tmp_path / "ckpt_last.pt", weights_only=False)
+    assert tuple(mine.keys()) == tuple(g["saved"].keys()) == iddm.CKPT_KEYS
+    for k in mine:
+        if k == "model":
+            assert all(torch.equal(mine[k][n], g["saved"][k][n]) for n in g["saved"][k]) and mine[k].keys() == g["saved"][k].keys()
+        elif k != "optimizer":
+            assert mine[k] == g["saved"][k], k
+    for c in g["cases"]:
+        ckpt_sd = toy(5, c["ckpt_prefix"]).state_dict()
+        model = toy(c["classes"], c["model_prefix"])
+        try:
+            iddm.load_model_ckpt(model, dict(ckpt_sd), is_train=c["is_train"], is_pretrain=c["is_pretrain"],
+                                 is_distributed=c["is_distributed"])
+            res = model.state_dict()
+        except Exception as e:
+            res = type(e).__name__
+        if isinstance(c["result"], str):
+            assert res == c["result"], c
+        else:
+            assert res.keys() == c["result"].keys() and all(torch.equal(res[k], v) for k, v in c["result"].items()), c
+    # load_ckpt: 'model' by default, 'ema_model' when it is the only one or when asked for; resumed training returns epoch + 1
+    tgt = toy(5)
+    assert iddm.load_ckpt(str(tmp_path / "ckpt_last.pt"), tgt, "cpu", is_train=False) is None
+    assert all(torch.equal(a, b) for a, b in zip(tgt.state_dict().values(), src.state_dict().values()))
+    opt2 = torch.optim.SGD(toy(5).parameters(), lr=0.1, momentum=0.9)
+    assert iddm.load_ckpt(str(tmp_path / "ckpt_last.pt"), toy(5), "cpu", optimizer=opt2, is_train=True) == 8

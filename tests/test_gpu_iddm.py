@@ -29,15 +29,18 @@ def build(iddm, size):
 
 
 @pytest.mark.parametrize("size", [32, 64])
-# bf16 is opt-in on this secondary path and NOT yet within the 2e-2 north-star tolerance (measured 2.6-3.2e-2 on
-# |eps| <= 2.6, i.e. ~1.2 % -- DESIGN.md section 5); the bound below only guards against regressions.
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 4e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_iddm_unet_forward(iddm, golden, size, precision, tol):
     g = golden("iddm.pt")[f"fwd_{size}"]
     net, chk = build(iddm, size)
     assert abs(chk - g["checksum"]) <= 1e-6 * chk
     net.set_precision(precision)
     x, t, y = g["x"].cuda(), g["t"].cuda(), g["y"].cuda()
+    if precision == "bf16":      # every attention block (head dims 16 / 32 / 64, T down to 16) is on the tcgen05 kernel
+        eng = net.engine(x.shape[0])
+        assert eng.attn_kinds == ["sm100"] * 6, eng.attn_kinds
+        names = [n for (_, _, n) in eng.L]
+        assert names.count("advs_conv_simt") == 0 and names.count("advs_conv_sm100_launch") >= 40
     e_c = net(x, t, y).cpu()
     e_u = net(x, t).cpu()
     err_c = (e_c - g["eps_cond"]).abs().max().item()
@@ -72,6 +75,32 @@ def test_iddm_cfg_ddim_sample(iddm, golden):
     frac_exact = (diff == 0).float().mean().item()
     print(f"IDDM CFG-DDIM 5 steps: uint8 image identical on {100 * frac_exact:.2f}% of values, max LSB diff {int(diff.max())}")
     assert int(diff.max()) <= 1 and frac_exact >= 0.995
+    net.release_engines()
+
+
+def test_iddm_cfg_one_forward_equals_two(iddm, golden):
+    """Classifier-free guidance as ONE forward over 2n rows (labels on the first n) == the reference's two forwards."""
+    g = golden("iddm.pt")["sample"]
+    net, _ = build(iddm, 32)
+    for precision in ("fp32", "bf16"):
+        net.set_precision(precision)
+        x, t, y = g["trace_x"][0].cuda(), g["trace_t"][0].cuda(), g["labels"].cuda()
+        n = x.shape[0]
+        e_c, e_u = net.engine(n).forward(x, t, y), net.engine(n).forward(x, t)
+        eng2 = net.engine(2 * n)
+        eng2.x.copy_(torch.cat([x, x])); eng2.t.copy_(torch.cat([t, t])); eng2.y[:n].copy_(y)
+        eng2.run(True, n_labeled=n)
+        torch.cuda.synchronize()
+        assert torch.equal(eng2.eps[:n], e_c) and torch.equal(eng2.eps[n:], e_u), precision
+    # and the 16-bit sampler end to end: 5 CFG steps stay close to the reference's fp32 image
+    ddim = iddm.DDIMDiffusion(noise_steps=1000, sample_steps=g["sample_steps"], img_size=32, device="cpu")
+    torch.manual_seed(5)
+    img = ddim.sample(net, 2, labels=g["labels"].cuda(), cfg_scale=g["cfg_scale"])
+    diff = (img.cpu().int() - g["image"].int()).abs()
+    diff = torch.minimum(diff, 256 - diff)
+    print(f"IDDM CFG-DDIM 5 steps, 16-bit mode: uint8 image identical on {100 * (diff == 0).float().mean().item():.2f}% of values, "
+          f"max LSB diff {int(diff.max())}, mean {diff.float().mean().item():.3f}")
+    assert diff.float().mean().item() < 10.0      # free-running, guidance scale 3: a sanity bound, not a parity claim
     net.release_engines()
 
 

@@ -704,3 +704,69 @@ def test_conv_fp16_operands(ops, case, f16):
         cp.operand_f16 = bad
         with pytest.raises(capi.AdvsError):
             capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
+
+
+def attn_ref(q, k, vt):
+    B, heads, T, dh = q.shape
+    p = torch.einsum("bhtd,bhsd->bhts", q.float(), k.float()).softmax(-1)
+    return torch.einsum("bhts,bhds->bthd", p, vt.float()).reshape(B, T, heads * dh)
+
+
+@pytest.mark.parametrize("T", [8, 64, 200, 784, 3136])       # 28x28 and 56x56 maps of a 224x224 input, and tiny maps
+@pytest.mark.parametrize("dh", [64, 128, 256])
+def test_attention_partial_last_key_block(ops, T, dh):
+    """T % 128 != 0 stays on the tcgen05 kernel: out-of-range keys of the last block are masked to -inf, query rows
+    past T are not stored.  Several (image, head) pairs so that the rows a partial block over-reads belong to the
+    NEXT head (finite garbage) for all but the last one (TMA zero fill)."""
+    torch.manual_seed(61)
+    B, heads = 2, 3
+    q = (torch.randn(B, heads, T, dh, device="cuda") * 0.8).to(torch.bfloat16)
+    k = (torch.randn(B, heads, T, dh, device="cuda") * 0.8).to(torch.bfloat16)
+    vt = torch.randn(B, heads, dh, T, device="cuda").to(torch.bfloat16)
+    guard = torch.full((B, T + 16, heads * dh), 7.0, dtype=torch.bfloat16, device="cuda")      # catches rows stored past T
+    o = ops.attention(q, k, vt, impl="sm100")
+    assert torch.isfinite(o.float()).all()
+    assert rel_err(o, attn_ref(q, k, vt)) < 1.5e-2
+    assert torch.equal(o, ops.attention(q, k, vt, impl="sm100"))
+    del guard
+
+
+@pytest.mark.parametrize("dhv", [16, 32])
+@pytest.mark.parametrize("T", [64, 256, 1000, 4096])
+def test_attention_padded_head_dim(ops, dhv, T):
+    """IDDM's 4-head nn.MultiheadAttention has head dims 16 / 32 (model/modules/attention.py:27): run as dh = 64 with
+    zero-padded q / k / v^T; the output holds the dh_valid real columns of every head, packed."""
+    torch.manual_seed(62)
+    B, heads = 2, 4
+    q = torch.zeros(B, heads, T, 64, dtype=torch.bfloat16, device="cuda")
+    k = torch.zeros_like(q)
+    vt = torch.zeros(B, heads, 64, T, dtype=torch.bfloat16, device="cuda")
+    q[..., :dhv] = (torch.randn(B, heads, T, dhv, device="cuda") * 0.9).to(torch.bfloat16)
+    k[..., :dhv] = (torch.randn(B, heads, T, dhv, device="cuda") * 0.9).to(torch.bfloat16)
+    vt[:, :, :dhv] = torch.randn(B, heads, dhv, T, device="cuda").to(torch.bfloat16)
+    o = ops.attention(q, k, vt, impl="sm100", dh_valid=dhv)
+    assert o.shape == (B, T, heads * dhv)
+    ref = attn_ref(q[..., :dhv], k[..., :dhv], vt[:, :, :dhv])
+    assert rel_err(o, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("c,heads,pad", [(64, 4, 64), (128, 4, 64), (128, 4, 0)])
+def test_conv_qkv_split_small_heads(ops, c, heads, pad):
+    """qkv epilogue for head dims 16 / 32, written into 64-wide zero-padded q / k / v^T (advs_conv_params.qkv_dh_pad)."""
+    torch.manual_seed(63)
+    B, H, W = 2, 16, 8
+    dh = c // heads
+    x = torch.randn(B, H, W, c, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(3 * c, c, 1, 1, device="cuda") / 8).to(torch.bfloat16).float()
+    bias = torch.randn(3 * c, device="cuda")
+    q, k, vt = ops.conv([(x, ops.pack_conv_weight(w, torch.bfloat16))], B, H, W, 3 * c, bias=bias, qkv_heads=heads, impl="sm100",
+                        qkv_dh_pad=pad)
+    ref = conv_ref(x, w, 1, bias).reshape(B, heads, 3, dh, H * W)
+    s_ = 1 / math.sqrt(math.sqrt(dh))
+    dhs = max(dh, pad)
+    assert q.shape == (B, heads, H * W, dhs) and vt.shape == (B, heads, dhs, H * W)
+    assert rel_err(q[..., :dh], (ref[:, :, 0] * s_).transpose(2, 3)) < 1e-2
+    assert rel_err(k[..., :dh], (ref[:, :, 1] * s_).transpose(2, 3)) < 1e-2
+    assert rel_err(vt[:, :, :dh], ref[:, :, 2]) < 1e-2
+    if dhs > dh:
+        assert float(q[..., dh:].abs().max()) == 0 and float(k[..., dh:].abs().max()) == 0 and float(vt[:, :, dh:].abs().max()) == 0

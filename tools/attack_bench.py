@@ -42,7 +42,8 @@ def main():
     gd = diff_model.GaussianDiffusion(timesteps=1000)
     victim = getattr(torchvision.models, args.victim)(num_classes=37).eval().to(dev)
     sampler = ShadowSampler(model, gd, n_img * K, S, ddim_timesteps=args.ddim_steps)
-    loop = AttackLoop(sampler, victim, candidates=K, victim_size=224)
+    kinds = sorted({nm for (_, _, nm) in sampler.eng._launches})
+    loop = AttackLoop(sampler, victim, candidates=K, victim_size=224, pad_to=-(-args.images // world))
     g = torch.Generator().manual_seed(7)          # same global data on every rank, sliced by shard
     clean = torch.rand(args.images, 3, S, S, generator=g)[lo:hi].repeat_interleave(K, 0)
     labels = torch.randint(0, 37, (args.images,), generator=g)[lo:hi].repeat_interleave(K, 0)
@@ -73,7 +74,9 @@ def main():
         print(json.dumps({"victim": args.victim, "gpus": world, "images": args.images, "candidates": K, "size": S,
                           "ddim_steps": args.ddim_steps, "trajectories_per_s": round(args.images * K * args.reps / (float(ms) / 1e3), 2),
                           "images_per_s": round(args.images * args.reps / (float(ms) / 1e3), 2), "asr": res["asr"],
-                          "flags_gathered": int(res["flags"].numel()), "decisions_match_torch": ok}))
+                          "flags_gathered": int(res["flags"].numel()), "decisions_match_torch": ok,
+                          "ms_per_batch": round(float(ms) / args.reps, 1), "kernel_classes": kinds,
+                          "arena_gb": round(sampler.eng.plan.arena_bytes / 2 ** 30, 1)}))
     if world > 1:
         dist.destroy_process_group()
 
