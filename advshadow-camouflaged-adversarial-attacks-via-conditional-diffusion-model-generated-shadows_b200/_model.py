@@ -150,7 +150,7 @@ class UNetModelBase(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, B, H, W, precision=None, conv_impl="auto", attn_impl="auto", fuse_gn_stats=True,
-               fuse_upsample=True, instance=0, wide_prenorm=2, gemm_operands="fp16"):
+               fuse_upsample=True, instance=0, wide_prenorm=2, gemm_operands="fp16", fp16_levels=2):
         """The (cached) UNetEngine for this input geometry; repacks weights if parameters changed.
         `instance` distinguishes independent engines of the same geometry (own arenas, for multi-stream use)."""
         from .engine import UNetEngine
@@ -164,13 +164,13 @@ class UNetModelBase(nn.Module):
                           "Dropout as identity (call model.eval(), as main.py:116 does)")
             self._warned_dropout = True
         key = (B, H, W, precision, conv_impl, attn_impl, fuse_gn_stats, fuse_upsample, dev.index, instance, wide_prenorm,
-               gemm_operands)
+               gemm_operands, fp16_levels)
         params = dict(self.named_parameters())
         tok = self._weights_token()
         hit = self._engines.get(key)
         if hit is None:
             eng = UNetEngine(self.spec(), params, B, H, W, precision, conv_impl, attn_impl, fuse_gn_stats, fuse_upsample,
-                             wide_prenorm, gemm_operands)
+                             wide_prenorm, gemm_operands, fp16_levels)
             self._engines[key] = [eng, tok]
             return eng
         if hit[1] != tok:

@@ -170,17 +170,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // once more when the normalised value is rounded for the GEMM.  Such tensors keep a companion int8 tensor with
 // the next 8 mantissa bits: v ~= bits(hi) + (lo << 8) as an integer add on the fp32 bit pattern -- IEEE bit
 // patterns are monotone in the magnitude, so the add carries correctly across binades and needs no exponent
-// arithmetic.  hi stays the round-to-nearest bf16 (it is also a GEMM operand and the residual); |v - decoded| <=
-// 2^-17 |v|.
-__device__ __forceinline__ int wide_lo_term(float v, uint32_t hi_bits32) {
-  // (difference in fp32 ulps, in [-2^15, 2^15]) + rounding offset, clamped so that byte 1 is the int8 to store
-  return min((int)(__float_as_uint(v) - hi_bits32) + 128, 32767);
-}
-// four consecutive values v[0..3] and their two packed bf16x2 words -> four int8 in one word
-__device__ __forceinline__ uint32_t wide_encode4(const float* v, uint32_t w01, uint32_t w23) {
-  const int t0 = wide_lo_term(v[0], w01 << 16), t1 = wide_lo_term(v[1], w01 & 0xFFFF0000u);
-  const int t2 = wide_lo_term(v[2], w23 << 16), t3 = wide_lo_term(v[3], w23 & 0xFFFF0000u);
-  return __byte_perm(__byte_perm(t0, t1, 0x0051), __byte_perm(t2, t3, 0x0051), 0x5410);
+// arithmetic.  Encoding is integer-only and cheaper than the plain bf16 conversion it replaces:
+//   u  = bits(v) + 0x8000          hi = u >> 16   (bf16 rounded to nearest, ties away from zero)
+//   lo = int8((u >> 8) & 0xFF) - 128 = byte 1 of u, sign bit flipped      (floor of the signed remainder / 256)
+// hi is also a GEMM operand and the residual for every other consumer; |v - decoded| < 2^-16 |v|.
+__device__ __forceinline__ uint32_t wide_round_bits(float v) { return __float_as_uint(v) + 0x8000u; }
+// two rounded bit patterns -> packed bf16x2 (their upper halves)
+__device__ __forceinline__ uint32_t wide_hi2(uint32_t u0, uint32_t u1) { return __byte_perm(u0, u1, 0x7632); }
+// four rounded bit patterns -> four int8 extensions in one word
+__device__ __forceinline__ uint32_t wide_lo4(uint32_t u0, uint32_t u1, uint32_t u2, uint32_t u3) {
+  return __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410) ^ 0x80808080u;
 }
 // element k (0..3) of a packed int8 word as (int)lo << 8
 // (one PRMT: result bytes = {0, byte K, sign(byte K), sign(byte K)}; the sign-replication bit of the selector

@@ -16,13 +16,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "sm100.cuh"
 #include "conv_sm100_common.cuh"
 
 namespace advs {
 
-template <int BN>
+template <int BN, bool A0F16>
 __global__ void __launch_bounds__(kConvThreads, 1)
 k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   using Cfg = ConvCfg<BN>;
@@ -108,8 +110,9 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp walks the schedule, one elected lane issues) =================
     {
-      const uint32_t idesc0 = umma_idesc_f16kind(128, BN, (a.operand_f16 & 1) != 0, (a.operand_f16 & 4) != 0);
-      const uint32_t idesc1 = umma_idesc_f16kind(128, BN, (a.operand_f16 & 2) != 0, (a.operand_f16 & 8) != 0);
+      // segment 0 in fp16 or bf16 (compile-time), shortcut segments always bf16: the descriptors stay immediates
+      constexpr uint32_t idesc0 = umma_idesc_f16kind(128, BN, A0F16, A0F16);
+      constexpr uint32_t idesc1 = umma_idesc_f16kind(128, BN, false, false);
       const int kb_seg0 = a.taps[0] * a.cblks[0];
       int stage = 0;
       uint32_t phase = 0;
@@ -119,13 +122,15 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < a.total_kb; ++kb) {
+        // compile-time instruction descriptors (see conv_sm100_halo.cu): K blocks of segment 0, then the shortcut segments
+        auto k_blocks = [&](const int kb_lo, const int kb_hi, auto idesc_c) {
+          constexpr uint32_t idesc = decltype(idesc_c)::value;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
-          const uint32_t idesc = kb < kb_seg0 ? idesc0 : idesc1;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 B) per 64-channel block
@@ -134,6 +139,13 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        };
+        if constexpr (A0F16) {
+          k_blocks(0, kb_seg0, std::integral_constant<uint32_t, idesc0>{});
+          k_blocks(kb_seg0, a.total_kb, std::integral_constant<uint32_t, idesc1>{});
+        } else {
+          k_blocks(0, a.total_kb, std::integral_constant<uint32_t, idesc0>{});
         }
         if (elect_one()) umma_commit(&tfull[acc]);
         __syncwarp();
@@ -165,6 +177,7 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool want_stats = a.stats != nullptr;
+      const bool wide = a.epi.y_lo != nullptr;
 #pragma unroll 1
       for (int chunk = col_half * (BN / 64); chunk < (col_half + 1) * (BN / 64); ++chunk) {
         uint32_t r[32];
@@ -175,7 +188,8 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
         float v[32];
         if (valid) {
           epilogue_compute32(a.epi, r, v, m, b, n);
-          epilogue_write32(a.epi, v, m, b, t, n);
+          if (wide) epilogue_write32<true>(a.epi, v, m, b, t, n);
+          else epilogue_write32<false>(a.epi, v, m, b, t, n);
         }
         if (want_stats) {
           // GroupNorm statistics of the tensor just written (taken before the bf16 rounding: the rounding
@@ -324,12 +338,10 @@ int advs_conv_sm100_plan(const advs_conv_params* p, void* plan_host) {
   a.stats = p->stats_partial;
   a.stats_gran = p->stats_gran == 4 ? 4 : 1;
   a.operand_f16 = p->operand_f16;
-  ADVS_CHECK_ARG((p->operand_f16 & ~15) == 0, "conv_sm100_plan: operand_f16 has unknown bits");
-  // tcgen05.mma kind::f16 with different A and B formats is an illegal instruction on sm_100 (tools/gpu/probe_mixed_mma.py)
-  ADVS_CHECK_ARG(((p->operand_f16 & 1) != 0) == ((p->operand_f16 & 4) != 0),
-                 "conv_sm100_plan: segment 0 activations and weights must have the same 16-bit format");
-  ADVS_CHECK_ARG(p->nseg == 1 || ((p->operand_f16 & 2) != 0) == ((p->operand_f16 & 8) != 0),
-                 "conv_sm100_plan: shortcut activations and weights must have the same 16-bit format");
+  // tcgen05.mma kind::f16 with different A and B formats is an illegal instruction on sm_100 (tools/gpu/probe_mixed_mma.py),
+  // and the shortcut segments read the unbounded residual stream: only "segment 0 entirely fp16" exists
+  ADVS_CHECK_ARG(p->operand_f16 == 0 || p->operand_f16 == 5,
+                 "conv_sm100_plan: operand_f16 must be 0 or 5 (segment 0: activations AND weights in fp16)");
   if (a.stats) {
     ADVS_CHECK_ARG(p->stats_gran == 0 || p->stats_gran == 1 || p->stats_gran == 4, "conv_sm100_plan: stats_gran must be 0, 1 or 4");
     ADVS_CHECK_ARG(p->out_mode == 0, "conv_sm100_plan: stats_partial needs out_mode 0");
@@ -412,10 +424,14 @@ int advs_conv_sm100_launch(const void* plan_host, void* stream) {
   if (plan->halo) return launch_conv_2cta_halo(plan, (cudaStream_t)stream);
   if (plan->two_cta) return launch_conv_2cta(plan, (cudaStream_t)stream);
   if (first_use_on_device(kOnceConv1Cta)) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg<128>::smem_bytes);
-    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg<256>::smem_bytes);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv_sm100<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ConvCfg<128>::smem_bytes);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_conv_sm100<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ConvCfg<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       forget_first_use(kOnceConv1Cta);
       set_error("conv_sm100_launch: cudaFuncSetAttribute failed: %s",
@@ -423,10 +439,15 @@ int advs_conv_sm100_launch(const void* plan_host, void* stream) {
       return ADVS_ERR_CUDA;
     }
   }
-  if (plan->bn == 256)
-    k_conv_sm100<256><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);
-  else
-    k_conv_sm100<128><<<plan->grid, kConvThreads, plan->smem_bytes, (cudaStream_t)stream>>>(plan->maps, plan->args);
+  const bool f16 = plan->args.operand_f16 != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->bn == 256) {
+    if (f16) k_conv_sm100<256, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    else k_conv_sm100<256, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  } else {
+    if (f16) k_conv_sm100<128, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    else k_conv_sm100<128, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  }
   ADVS_CHECK_LAUNCH("conv_sm100_launch");
   return ADVS_OK;
 }

@@ -16,6 +16,8 @@
 //   tempty[a] leader's copy only: 16 arrivals (8 epilogue warps x 2 CTAs)
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "sm100.cuh"
 #include "conv_sm100_common.cuh"
@@ -33,7 +35,7 @@ struct ConvCfg2 {
   static constexpr uint32_t tmem_cols = 2 * BN;
 };
 
-template <int BN>
+template <int BN, bool A0F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   using Cfg = ConvCfg2<BN>;
@@ -126,8 +128,9 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader) {   // the whole warp walks the schedule; one elected lane issues (warp-uniform control flow)
-      const uint32_t idesc0 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 1) != 0, (a.operand_f16 & 4) != 0);
-      const uint32_t idesc1 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 2) != 0, (a.operand_f16 & 8) != 0);
+      // segment 0 in fp16 or bf16 (compile-time), shortcut segments always bf16: the descriptors stay immediates
+      constexpr uint32_t idesc0 = umma_idesc_f16kind(256, BN, A0F16, A0F16);
+      constexpr uint32_t idesc1 = umma_idesc_f16kind(256, BN, false, false);
       const int kb_seg0 = a.taps[0] * a.cblks[0];
       int stage = 0;
       uint32_t phase = 0;
@@ -137,13 +140,15 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < a.total_kb; ++kb) {
+        // compile-time instruction descriptors (see conv_sm100_halo.cu): K blocks of segment 0, then the shortcut segments
+        auto k_blocks = [&](const int kb_lo, const int kb_hi, auto idesc_c) {
+          constexpr uint32_t idesc = decltype(idesc_c)::value;
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::stage_bytes);
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + kABytes);
-          const uint32_t idesc = kb < kb_seg0 ? idesc0 : idesc1;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -152,6 +157,13 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        };
+        if constexpr (A0F16) {
+          k_blocks(0, kb_seg0, std::integral_constant<uint32_t, idesc0>{});
+          k_blocks(kb_seg0, a.total_kb, std::integral_constant<uint32_t, idesc1>{});
+        } else {
+          k_blocks(0, a.total_kb, std::integral_constant<uint32_t, idesc0>{});
         }
         if (elect_one()) umma_commit_2cta(&tfull[acc], 3);
         __syncwarp();
@@ -183,6 +195,7 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool want_stats = a.stats != nullptr;
+      const bool wide = a.epi.y_lo != nullptr;
 #pragma unroll 1
       for (int chunk = col_half * (BN / 64); chunk < (col_half + 1) * (BN / 64); ++chunk) {
         uint32_t r[32];
@@ -193,7 +206,8 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
         float v[32];
         if (valid) {
           epilogue_compute32(a.epi, r, v, m, b, n);
-          epilogue_write32(a.epi, v, m, b, t, n);
+          if (wide) epilogue_write32<true>(a.epi, v, m, b, t, n);
+          else epilogue_write32<false>(a.epi, v, m, b, t, n);
         }
         if (want_stats) {
           // GroupNorm statistics of the tensor just written (taken before the bf16 rounding: the rounding
@@ -222,20 +236,28 @@ uint32_t conv_2cta_smem_bytes(int bn) { return bn == 256 ? ConvCfg2<256>::smem_b
 
 int launch_conv_2cta(const ConvPlan* plan, cudaStream_t st) {
   if (first_use_on_device(kOnceConv2Cta)) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg2<128>::smem_bytes);
-    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfg2<256>::smem_bytes);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv_sm100_2cta<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ConvCfg2<128>::smem_bytes);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_conv_sm100_2cta<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ConvCfg2<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_error("conv_sm100_launch(2cta): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       forget_first_use(kOnceConv2Cta);
       return ADVS_ERR_CUDA;
     }
   }
-  if (plan->bn == 256)
-    k_conv_sm100_2cta<256><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-  else
-    k_conv_sm100_2cta<128><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  const bool f16 = plan->args.operand_f16 != 0;
+  if (plan->bn == 256) {
+    if (f16) k_conv_sm100_2cta<256, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    else k_conv_sm100_2cta<256, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  } else {
+    if (f16) k_conv_sm100_2cta<128, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    else k_conv_sm100_2cta<128, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  }
   ADVS_CHECK_LAUNCH("conv_sm100_launch(2cta)");
   return ADVS_OK;
 }

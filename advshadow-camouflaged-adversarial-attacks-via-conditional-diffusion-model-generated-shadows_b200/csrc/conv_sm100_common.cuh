@@ -25,7 +25,7 @@ struct ConvArgs {
   int stats_tpi, stats_rpi, stats_off;   // row = (m_tile / tpi) * rpi + off + m_tile % tpi
   int stats_gran;                        // 1: one {sum, sumsq} per channel; 4: per 4 consecutive channels
   int up_a, up_b, up;                    // upsample phase: output pixel (2h+a, 2w+b); up = 0/1
-  int operand_f16;                       // advs_conv_params.operand_f16 (bits 0/1: A of segment 0 / 1..2, bits 2/3: B of segment 0 / 1..2)
+  int operand_f16;                       // advs_conv_params.operand_f16: 0, or 5 = segment 0 (activations and weights) in fp16
   EpilogueParams epi;
 };
 
@@ -107,60 +107,88 @@ __device__ __forceinline__ void epilogue_compute32(const EpilogueParams& e, cons
   }
 }
 
+// WIDE: also store the int8 mantissa extension (e.y_lo != nullptr).  A template parameter, chosen by a warp-uniform
+// branch at the call site: with a run-time `if (e.y_lo)` inside the unrolled loops ptxas predicated the encoder
+// into every instantiation and the plain epilogue lost 25 % (profiles/microbench_r02.md).
+template <bool WIDE>
 __device__ __forceinline__ void epilogue_write32(const EpilogueParams& e, const float* v, size_t m, int b, int t, int n) {
   if (e.out_mode == 0) {
     __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(e.y) + m * e.Cout + n;
-    uint32_t lo8[8];
+    if constexpr (WIDE) {
+      uint32_t lo8[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      uint32_t o[8];
+      for (int j = 0; j < 2; ++j) {
+        uint32_t u[16], o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
-      st_global_256(yp + 16 * j, o);
-      if (e.y_lo) {
+        for (int i = 0; i < 16; ++i) u[i] = wide_round_bits(v[16 * j + i]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) lo8[4 * j + i] = wide_encode4(v + 16 * j + 4 * i, o[2 * i], o[2 * i + 1]);
+        for (int i = 0; i < 8; ++i) o[i] = wide_hi2(u[2 * i], u[2 * i + 1]);
+        st_global_256(yp + 16 * j, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lo8[4 * j + i] = wide_lo4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+      }
+      st_global_256(e.y_lo + m * e.Cout + n, lo8);   // 32 channels x int8
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
+        st_global_256(yp + 16 * j, o);
       }
     }
-    if (e.y_lo) st_global_256(e.y_lo + m * e.Cout + n, lo8);   // 32 channels x int8
   } else if (e.out_mode == 2) {
     float* dst = reinterpret_cast<float*>(e.y) + ((size_t)b * e.cout_valid + n) * e.HW + t;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (n + j < e.cout_valid) dst[(size_t)j * e.HW] = v[j];
+  } else if (e.dh >= 32) {
+    // 32 consecutive output channels = one piece of a head's [q | k | v] block
+    const int head = n / (3 * e.dh);
+    const int r = n - head * 3 * e.dh;
+    const int which = r / e.dh;
+    const int d0 = r - which * e.dh;
+    const size_t bh = (size_t)b * e.heads + head;
+    if (which < 2) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh_pad + d0;
+      uint4* yp = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[8 * j] * e.qk_scale, v[8 * j + 1] * e.qk_scale);
+        o.y = pack_bf16x2(v[8 * j + 2] * e.qk_scale, v[8 * j + 3] * e.qk_scale);
+        o.z = pack_bf16x2(v[8 * j + 4] * e.qk_scale, v[8 * j + 5] * e.qk_scale);
+        o.w = pack_bf16x2(v[8 * j + 6] * e.qk_scale, v[8 * j + 7] * e.qk_scale);
+        yp[j] = o;
+      }
+    } else {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh_pad + d0) * e.HW + t;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[(size_t)j * e.HW] = __float2bfloat16_rn(v[j]);
+    }
   } else {
-    // 32 consecutive output channels = one piece of a head's [q | k | v] block, or two 16-wide pieces when dh = 16
-    const int g = e.dh >= 32 ? 32 : 16;
+    // head dim 16 (IDDM): the 32 channels are two 16-wide pieces of (possibly different) q / k / v blocks
 #pragma unroll
     for (int sub = 0; sub < 2; ++sub) {
-      if (sub * g >= 32) break;
-      const int nn = n + sub * g;
+      const int nn = n + sub * 16;
       const int head = nn / (3 * e.dh);
       const int r = nn - head * 3 * e.dh;
       const int which = r / e.dh;
       const int d0 = r - which * e.dh;
       const size_t bh = (size_t)b * e.heads + head;
-      const float* vv = v + sub * g;
+      const float* vv = v + sub * 16;
       if (which < 2) {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh_pad + d0;
-        uint4* yp = reinterpret_cast<uint4*>(dst);
+        uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(which == 0 ? e.q : e.k) + (bh * e.HW + t) * e.dh_pad + d0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (8 * j >= g) break;
-          uint4 o;
-          o.x = pack_bf16x2(vv[8 * j] * e.qk_scale, vv[8 * j + 1] * e.qk_scale);
-          o.y = pack_bf16x2(vv[8 * j + 2] * e.qk_scale, vv[8 * j + 3] * e.qk_scale);
-          o.z = pack_bf16x2(vv[8 * j + 4] * e.qk_scale, vv[8 * j + 5] * e.qk_scale);
-          o.w = pack_bf16x2(vv[8 * j + 6] * e.qk_scale, vv[8 * j + 7] * e.qk_scale);
-          yp[j] = o;
-        }
+        for (int j = 0; j < 2; ++j)
+          yp[j] = make_uint4(pack_bf16x2(vv[8 * j] * e.qk_scale, vv[8 * j + 1] * e.qk_scale),
+                             pack_bf16x2(vv[8 * j + 2] * e.qk_scale, vv[8 * j + 3] * e.qk_scale),
+                             pack_bf16x2(vv[8 * j + 4] * e.qk_scale, vv[8 * j + 5] * e.qk_scale),
+                             pack_bf16x2(vv[8 * j + 6] * e.qk_scale, vv[8 * j + 7] * e.qk_scale));
       } else {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.vt) + (bh * e.dh_pad + d0) * e.HW + t;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j >= g) break;
-          dst[(size_t)j * e.HW] = __float2bfloat16_rn(vv[j]);
-        }
+        for (int j = 0; j < 16; ++j) dst[(size_t)j * e.HW] = __float2bfloat16_rn(vv[j]);
       }
     }
   }

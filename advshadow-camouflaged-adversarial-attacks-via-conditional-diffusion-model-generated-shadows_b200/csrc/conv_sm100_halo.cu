@@ -9,6 +9,8 @@
 // L2-bandwidth bound at 795 TFLOP/s while BN = 256 layers reach 1 400.
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "sm100.cuh"
 #include "conv_sm100_common.cuh"
@@ -45,7 +47,7 @@ struct ConvCfgH {
   static constexpr uint32_t tmem_cols = 2 * BN;
 };
 
-template <int BN>
+template <int BN, bool A0F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   using Cfg = ConvCfgH<BN>;
@@ -136,8 +138,9 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
     if (leader) {   // the whole warp walks the schedule; one elected lane issues (warp-uniform control flow)
-      const uint32_t idesc0 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 1) != 0, (a.operand_f16 & 4) != 0);
-      const uint32_t idesc1 = umma_idesc_f16kind(256, BN, (a.operand_f16 & 2) != 0, (a.operand_f16 & 8) != 0);
+      // segment 0 in fp16 or bf16 (compile-time), shortcut segments always bf16: the descriptors stay immediates
+      constexpr uint32_t idesc0 = umma_idesc_f16kind(256, BN, A0F16, A0F16);
+      constexpr uint32_t idesc1 = umma_idesc_f16kind(256, BN, false, false);
       int stage = 0, abuf = 0;
       uint32_t phase = 0, aphase = 0;
       int acc = 0;
@@ -150,9 +153,11 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
         CTR(13);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         uint32_t first = 1;
-        for (int s = 0; s < a.nseg; ++s) {
+        // the instruction descriptor must stay an immediate / uniform register: a run-time select puts it into a
+        // vector register and costs an extra R2UR in front of every MMA group (this kernel is issue-bound at BN = 128)
+        auto segment = [&](const int s, auto idesc_c) {
+          constexpr uint32_t idesc = decltype(idesc_c)::value;
           const int taps = a.taps[s];
-          const uint32_t idesc = s == 0 ? idesc0 : idesc1;
           for (int cb = 0; cb < a.cblks[s]; ++cb) {
             mbar_wait(&a_full[abuf], aphase);
             const uint32_t a_base = smem_u32(smem + abuf * Cfg::a_buf_bytes);
@@ -187,7 +192,9 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
             __syncwarp();
             if (++abuf == Cfg::a_bufs) { abuf = 0; aphase ^= 1; }
           }
-        }
+        };
+        segment(0, std::integral_constant<uint32_t, idesc0>{});
+        for (int s = 1; s < a.nseg; ++s) segment(s, std::integral_constant<uint32_t, idesc1>{});
         if (elect_one()) umma_commit_2cta(&tfull[acc], 3);
         __syncwarp();
         CTR(14);
@@ -222,6 +229,7 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
       CTR(1);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
       const bool want_stats = a.stats != nullptr;
+      const bool wide = a.epi.y_lo != nullptr;
 #pragma unroll 1
       for (int chunk = col_half * (BN / 64); chunk < (col_half + 1) * (BN / 64); ++chunk) {
         uint32_t r[32];
@@ -234,7 +242,8 @@ k_conv_sm100_2cta_halo(const __grid_constant__ ConvMaps maps, const ConvArgs a) 
         if (valid) {
           epilogue_compute32(a.epi, r, v, m, b, n);
           if (chunk == 0) CTR(3);
-          epilogue_write32(a.epi, v, m, b, t, n);
+          if (wide) epilogue_write32<true>(a.epi, v, m, b, t, n);
+          else epilogue_write32<false>(a.epi, v, m, b, t, n);
           if (chunk == 0) CTR(4);
         }
         if (want_stats) {
@@ -277,20 +286,28 @@ uint32_t conv_2cta_halo_smem_bytes(int bn) { return bn == 256 ? ConvCfgH<256>::s
 
 int launch_conv_2cta_halo(const ConvPlan* plan, cudaStream_t st) {
   if (first_use_on_device(kOnceConvHalo)) {
-    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e1 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfgH<128>::smem_bytes);
-    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e2 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ConvCfgH<256>::smem_bytes);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ConvCfgH<128>::smem_bytes);
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(k_conv_sm100_2cta_halo<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     ConvCfgH<256>::smem_bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_error("conv_sm100_launch(halo): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       forget_first_use(kOnceConvHalo);
       return ADVS_ERR_CUDA;
     }
   }
-  if (plan->bn == 256)
-    k_conv_sm100_2cta_halo<256><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-  else
-    k_conv_sm100_2cta_halo<128><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  const bool f16 = plan->args.operand_f16 != 0;
+  if (plan->bn == 256) {
+    if (f16) k_conv_sm100_2cta_halo<256, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    else k_conv_sm100_2cta_halo<256, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  } else {
+    if (f16) k_conv_sm100_2cta_halo<128, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    else k_conv_sm100_2cta_halo<128, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+  }
   ADVS_CHECK_LAUNCH("conv_sm100_launch(halo)");
   return ADVS_OK;
 }

@@ -12,14 +12,15 @@ __device__ __forceinline__ void epilogue_store1(const EpilogueParams& e, size_t 
   if (e.temb) v += e.temb[(size_t)b * e.temb_stride + n];
   if (e.out_mode == 0) {
     if (e.residual) v += to_f(reinterpret_cast<const T*>(e.residual)[m * e.Cout + n]);
-    const T hv = from_f<T>(v);
-    reinterpret_cast<T*>(e.y)[m * e.Cout + n] = hv;
     if constexpr (sizeof(T) == 2) {
       if (e.y_lo) {   // "wide" pre-norm storage, see common.cuh
-        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hv) << 16;
-        e.y_lo[m * e.Cout + n] = (uint8_t)((uint32_t)wide_lo_term(v, hb) >> 8);
+        const uint32_t u = wide_round_bits(v);
+        reinterpret_cast<uint16_t*>(e.y)[m * e.Cout + n] = (uint16_t)(u >> 16);
+        e.y_lo[m * e.Cout + n] = (uint8_t)(((u >> 8) & 0xFFu) ^ 0x80u);
+        return;
       }
     }
+    reinterpret_cast<T*>(e.y)[m * e.Cout + n] = from_f<T>(v);
   } else if (e.out_mode == 2) {
     if (n < e.cout_valid) reinterpret_cast<float*>(e.y)[((size_t)b * e.cout_valid + n) * e.HW + t] = v;
   } else {

@@ -28,7 +28,7 @@ class UNetEngine:
 
     def __init__(self, spec: UNetSpec, params: Dict[str, torch.Tensor], B: int, H: int, W: int,
                  precision: str = "bf16", conv_impl: str = "auto", attn_impl: str = "auto", fuse_gn_stats: bool = True,
-                 fuse_upsample: bool = True, wide_prenorm: int = 2, gemm_operands: str = "fp16"):
+                 fuse_upsample: bool = True, wide_prenorm: int = 2, gemm_operands: str = "fp16", fp16_levels: int = 2):
         """`wide_prenorm`: bf16 mode only -- tensors of the `wide_prenorm` highest-resolution levels that a GroupNorm
         reads (residual stream, conv1 outputs, skips) are stored as bf16 + an int8 mantissa extension
         (advs_conv_params.y_lo), so the value entering the normalisation carries 16 mantissa bits like the
@@ -41,7 +41,11 @@ class UNetEngine:
         the stem's im2col rows of the (bounded) sampler state are fp16 too.  Activations whose range is not bounded
         -- conv outputs, the residual stream, q/k/v, attention output -- stay bf16, and so do the weights multiplying
         them: the hardware rejects an MMA whose two operands differ in format (tools/gpu/probe_mixed_mma.py:
-        illegal instruction).  "bf16" makes every operand bf16."""
+        illegal instruction).  "bf16" makes every operand bf16.
+        `fp16_levels`: fp16 operands are used on that many top-resolution levels only.  The deeper levels hold most
+        of the FLOPs and contribute almost nothing to the output error (their dot products are 9 x 512 ... 9 x 2048
+        terms long and their errors are averaged again on the way up), while fp16 MMAs draw measurably more power
+        than bf16 ones: under the 1 kW cap the all-fp16 variant clocked 3 % lower (profiles/ab_r02.md)."""
         if precision not in _DT:
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
         any_p = next(iter(params.values()))
@@ -112,8 +116,10 @@ class UNetEngine:
                 self._stat_buf[a["dst"]] = (name, parts, gran)
         # fp16 GEMM operands: a GroupNorm output is fp16 when its (single) consumer is a tcgen05 conv / the head
         self._gn_f16 = set()
+        self.fp16_levels = fp16_levels
         if self.gemm_operands == "fp16":
-            gn_dst = {op.args["dst"] for op in plan.ops if op.kind == "gn"}
+            gn_dst = {op.args["dst"] for op in plan.ops
+                      if op.kind == "gn" and (plan.shape(op.args["dst"])[1] << fp16_levels) > H}
             for op in plan.ops:
                 a = op.args
                 if op.kind == "conv" and self._conv_sm100_ok(a) and a["segs"][0][0] in gn_dst:

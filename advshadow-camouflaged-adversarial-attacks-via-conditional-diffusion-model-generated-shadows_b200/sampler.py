@@ -32,7 +32,7 @@ def _st():
 class ShadowSampler:
     def __init__(self, model: UNetModelBase, diffusion, batch_size, image_size, ddim_timesteps=50,
                  ddim_discr_method="uniform", clip_denoised=True, precision=None, mask_channels=1, use_graph=True,
-                 streams=1, shadow_flavour="dm2", graph_scope="trajectory", _instance=0, _buffers=None):
+                 streams=1, shadow_flavour="dm2", graph_scope="trajectory", engine_options=None, _instance=0, _buffers=None):
         """`streams` > 1 splits the batch into that many independent sub-batches, each with its own engine and
         CUDA stream: the HBM-bound kernels of one sub-batch (GroupNorm apply, stem, ...) then overlap with the
         tensor-bound kernels of the other on the same SMs (they need no shared memory, the conv CTAs need it all).
@@ -40,7 +40,8 @@ class ShadowSampler:
         generated image injected as the adversarial image the shadow intensity drops out of the result, so the
         flavours differ only in the mask blur.
         `graph_scope`: "trajectory" (one CUDA graph holds all n steps and the composite) or "step" (one graph per
-        step, replayed n times from the host; kept for comparison)."""
+        step, replayed n times from the host; kept for comparison).
+        `engine_options`: keyword arguments for UNetModel.engine (wide_prenorm, gemm_operands, ...; A/B measurements)."""
         if not isinstance(model, UNetModelBase):
             raise TypeError("ShadowSampler needs an advshadow_b200 UNetModel")
         if streams > 1 and (batch_size % streams or batch_size // streams < 1):
@@ -55,6 +56,7 @@ class ShadowSampler:
         self.blur = 1 if SHADOW_FLAVOURS[shadow_flavour] else 0
         self.graph_scope = graph_scope
         self.precision = precision
+        self.engine_options = dict(engine_options or {})
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("ShadowSampler runs on CUDA only (no CPU path)")
@@ -80,14 +82,16 @@ class ShadowSampler:
                         self.children.append(ShadowSampler(model, diffusion, sub, image_size, ddim_timesteps,
                                                            ddim_discr_method, clip_denoised, precision, mask_channels,
                                                            use_graph, streams=1, shadow_flavour=shadow_flavour,
-                                                           graph_scope=graph_scope, _instance=i + 1, _buffers=bufs))
+                                                           graph_scope=graph_scope, engine_options=engine_options,
+                                                           _instance=i + 1, _buffers=bufs))
                 torch.cuda.synchronize(self.device)
             self.eng = self.children[0].eng
             self.launches_per_trajectory = sum(c.launches_per_trajectory for c in self.children)
             return
         with torch.cuda.device(self.device):
             self._instance = _instance
-            self.eng = model.engine(batch_size, image_size, image_size, precision=precision, instance=_instance)
+            self.eng = model.engine(batch_size, image_size, image_size, precision=precision, instance=_instance,
+                                    **self.engine_options)
             seq, prev = ddim_timestep_tables(diffusion.timesteps, ddim_timesteps, ddim_discr_method)
             self.coef = diffusion.ddim_coefficients(seq, prev, ddim_timesteps, 0.0).to(self.device)
             self.ts = torch.tensor([int(seq[i]) for i in reversed(range(ddim_timesteps))], dtype=torch.int64)
@@ -158,7 +162,8 @@ class ShadowSampler:
         """Weights changed since the tables were built (load_state_dict, optimiser step, in-place edit)?  Then the
         engine has re-packed them into its own buffers (model.engine does that) and the time-embedding table is
         recomputed in place; captured graphs only hold engine-owned addresses and stay valid."""
-        eng = self.model.engine(self.B, self.S, self.S, precision=self.precision, instance=self._instance)
+        eng = self.model.engine(self.B, self.S, self.S, precision=self.precision, instance=self._instance,
+                                **self.engine_options)
         if eng is not self.eng:       # the model dropped its engine cache (.to() / release_engines()): rebuild
             self.eng = eng
             self.table = eng.temb_table(self.ts)

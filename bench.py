@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--no-torch-gpu", action="store_true", help="skip the informative PyTorch-eager-on-GPU sample")
     ap.add_argument("--profile-repeats", type=int, default=20)
     ap.add_argument("--graph-scope", default="trajectory", choices=["trajectory", "step"])
+    ap.add_argument("--wide-prenorm", type=int, default=2, help="A/B: levels stored with the int8 mantissa extension (0 = off)")
+    ap.add_argument("--gemm-operands", default="fp16", choices=["fp16", "bf16"], help="A/B: format of the bounded GEMM operands")
+    ap.add_argument("--fp16-levels", type=int, default=2, help="A/B: top-resolution levels whose bounded operands are fp16")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("ADVS_BENCH_STREAMS", "2")),
                     help="independent sub-batches on separate CUDA streams inside ShadowSampler")
     return ap.parse_args()
@@ -52,7 +55,9 @@ def workload(args):
                         f"{args.size}x{args.size}, DDIM-{args.ddim_steps} eta=0, batch {args.batch}/GPU, "
                         f"+ fused shadow composite",
             "batch_per_gpu": args.batch, "image_size": args.size, "ddim_steps": args.ddim_steps,
-            "precision": args.precision, "streams": args.streams, "graph": f"one CUDA graph per {args.graph_scope}",
+            "precision": (f"16-bit: bf16 storage + int8 mantissa extension on the {args.wide_prenorm} top-resolution levels' pre-norm "
+                          f"tensors, {args.gemm_operands} bounded GEMM operands on the {args.fp16_levels} top levels, fp32 accumulate") if args.precision == "bf16" else args.precision,
+            "streams": args.streams, "graph": f"one CUDA graph per {args.graph_scope}",
             "l2": "per-forward activations (GBs) exceed the 126 MB L2",
             "parallelism": f"dp{args.gpus} (images sharded, no collective in the step loop)"}
 
@@ -271,7 +276,9 @@ def main():
     model = diff_model2.UNetModel().eval().to(dev)
     gd = diff_model2.GaussianDiffusion(timesteps=1000)
     sampler = ShadowSampler(model, gd, B, S, ddim_timesteps=n, precision=args.precision, streams=args.streams,
-                            graph_scope=args.graph_scope)
+                            graph_scope=args.graph_scope,
+                            engine_options=dict(wide_prenorm=args.wide_prenorm, gemm_operands=args.gemm_operands,
+                                                fp16_levels=args.fp16_levels))
 
     # synthetic batch (pinned host copies for the end-to-end leg)
     g = torch.Generator().manual_seed(1234 + rank)

@@ -175,15 +175,17 @@ typedef struct advs_conv_params {
    * a third of the epilogue's shuffles; usable whenever every GroupNorm reading the tensor has a multiple of 4
    * channels per group (pass the same value as gran to advs_groupnorm_finalize_ex). */
   int32_t stats_gran;
-  /* optional (out_mode 0, ADVS_BF16): "wide" storage for a tensor that a GroupNorm will read.  y stays the
-   * round-to-nearest bf16 tensor (GEMM operand / residual for every other consumer); y_lo[B,H,W,Cout] int8 holds
-   * the next 8 mantissa bits: value ~= as_float((bits(y) << 16) + ((int)y_lo << 8)), exact to 2^-17 relative.
+  /* optional (out_mode 0, ADVS_BF16): "wide" storage for a tensor that a GroupNorm will read.  y stays a
+   * round-to-nearest bf16 tensor (ties away from zero; GEMM operand / residual for every other consumer);
+   * y_lo[B,H,W,Cout] int8 holds the next 8 mantissa bits: value ~= as_float((bits(y) << 16) + ((int)y_lo << 8)),
+   * exact to 2^-16 relative.
    * advs_groupnorm_apply_wide reads the pair, so the normalised GEMM operand is rounded once instead of twice
    * (the reference normalises fp32 tensors, dm1:71-72, 83-84). */
   void* y_lo;
-  /* sm100 path: which GEMM operands are fp16 instead of bf16 (ADVS_F16 above): bit 0 = the activations of segment 0
-   * (a GroupNorm output written by advs_groupnorm_apply_wide with y_dtype = ADVS_F16), bit 1 = the activations of
-   * segments 1..2, bit 2 = the packed weights of segment 0, bit 3 = the packed weights of segments 1..2. */
+  /* sm100 path: 0 = every GEMM operand is bf16; 5 (bits 0 and 2) = segment 0 is an fp16 x fp16 GEMM: its activations
+   * are a bounded tensor written as ADVS_F16 (advs_groupnorm_apply_wide / advs_stem_im2col_ex) and its weights were
+   * packed as ADVS_F16.  The shortcut segments always stay bf16 x bf16; a segment whose two operands differ in
+   * format cannot be expressed (the hardware rejects such an MMA). */
   int32_t operand_f16;
   /* out_mode 1: storage head dim of q / k / vt when it is larger than dh = Cout / (3*heads) (0 = dh): the epilogue
    * writes the dh real columns of each head into rows of qkv_dh_pad elements (q, k) / into the first dh of

@@ -39,7 +39,7 @@ def _sm100_ok(plan, a):
 
 
 def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2, gemm_operands="fp16", mixed_mma=False,
-             exact_w=()):
+             exact_w=(), fp16_levels=2):
     """`wide_prenorm` (with round_bf16): conv outputs of that many top-resolution levels keep an unrounded copy that
     only GroupNorm reads (the engine's bf16 + int8 mantissa-extension storage, exact to 2^-17).
     `gemm_operands` = "fp16": GroupNorm outputs consumed by a tcgen05 conv, and the weights multiplying them, are
@@ -49,7 +49,9 @@ def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2, gemm_
     categories left unrounded ("stem", "shortcut", "upconv", "down", "proj"), same purpose."""
     rnd = (lambda t: t.to(torch.bfloat16).float()) if round_bf16 else (lambda t: t)
     r16 = (lambda t: t.to(torch.float16).float()) if (round_bf16 and gemm_operands == "fp16") else rnd
-    gn_dst = {op.args["dst"] for op in plan.ops if op.kind == "gn"}
+    # `fp16_levels`: fp16 operands only on that many top-resolution levels (None = all), engine.UNetEngine(fp16_levels=)
+    top = lambda buf: fp16_levels is None or (plan.shape(buf)[1] << fp16_levels) > plan.H
+    gn_dst = {op.args["dst"] for op in plan.ops if op.kind == "gn" and top(op.args["dst"])}
     gn_f16 = set()
     for op in plan.ops:
         a = op.args

