@@ -153,6 +153,7 @@ k_attention_sm100(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp < kAttnFirstSoftmaxWarp) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -409,7 +410,7 @@ static int attn_launch(const AttnPlan* plan, cudaStream_t st) {
     }
   }
   dim3 grid((plan->args.T + kBQ - 1) / kBQ, plan->args.B * plan->args.heads);
-  k_attention_sm100<DH><<<grid, kAttnThreads, AttnCfg<DH>::smem_bytes, st>>>(plan->maps, plan->args);
+  launch_pdl(k_attention_sm100<DH>, grid, dim3(kAttnThreads), AttnCfg<DH>::smem_bytes, st, plan->maps, plan->args);
   ADVS_CHECK_LAUNCH("attention_sm100_launch");
   return ADVS_OK;
 }

@@ -1,5 +1,6 @@
 // Library-level entry points + shared host-side validation.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -41,6 +42,11 @@ int current_device_sms() {
     g_sms[d].store(n);
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("ADVS_PDL"); return !e || atoi(e) != 0; }();
+  return on;
 }
 
 int validate_conv(const advs_conv_params* p, const char* who) {

@@ -60,6 +60,7 @@ k_conv_sm100(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();      // everything above overlapped the previous kernel's tail; from here on its results are visible
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -442,11 +443,11 @@ int advs_conv_sm100_launch(const void* plan_host, void* stream) {
   const bool f16 = plan->args.operand_f16 != 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->bn == 256) {
-    if (f16) k_conv_sm100<256, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-    else k_conv_sm100<256, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    if (f16) launch_pdl(k_conv_sm100<256, true>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
+    else launch_pdl(k_conv_sm100<256, false>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
   } else {
-    if (f16) k_conv_sm100<128, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-    else k_conv_sm100<128, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    if (f16) launch_pdl(k_conv_sm100<128, true>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
+    else launch_pdl(k_conv_sm100<128, false>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
   }
   ADVS_CHECK_LAUNCH("conv_sm100_launch");
   return ADVS_OK;

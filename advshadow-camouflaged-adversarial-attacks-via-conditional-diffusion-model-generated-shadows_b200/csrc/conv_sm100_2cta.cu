@@ -76,6 +76,7 @@ k_conv_sm100_2cta(const __grid_constant__ ConvMaps maps, const ConvArgs a) {
   cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();      // everything above overlapped the previous kernel's tail; from here on its results are visible
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -252,11 +253,11 @@ int launch_conv_2cta(const ConvPlan* plan, cudaStream_t st) {
   }
   const bool f16 = plan->args.operand_f16 != 0;
   if (plan->bn == 256) {
-    if (f16) k_conv_sm100_2cta<256, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-    else k_conv_sm100_2cta<256, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    if (f16) launch_pdl(k_conv_sm100_2cta<256, true>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
+    else launch_pdl(k_conv_sm100_2cta<256, false>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
   } else {
-    if (f16) k_conv_sm100_2cta<128, true><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
-    else k_conv_sm100_2cta<128, false><<<plan->grid, kConvThreads, plan->smem_bytes, st>>>(plan->maps, plan->args);
+    if (f16) launch_pdl(k_conv_sm100_2cta<128, true>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
+    else launch_pdl(k_conv_sm100_2cta<128, false>, dim3(plan->grid), dim3(kConvThreads), plan->smem_bytes, st, plan->maps, plan->args);
   }
   ADVS_CHECK_LAUNCH("conv_sm100_launch(2cta)");
   return ADVS_OK;

@@ -84,6 +84,7 @@ template <int CIN, bool F16 = false>
 __global__ void __launch_bounds__(kStemPixPerBlock)
 k_stem_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int B, int H, int W, int cin_rt, int parts) {
   __shared__ __align__(16) uint8_t rows[kStemPixPerBlock * kStemPitch];
+  pdl_sync();
   const int Cin = CIN > 0 ? CIN : cin_rt;
   const size_t npix = (size_t)B * H * W;
   const size_t pix0 = (size_t)blockIdx.x * kStemPixPerBlock;
@@ -316,6 +317,7 @@ __global__ void k_upsample2x(const T* __restrict__ x, T* __restrict__ y, int B, 
 __global__ void k_ddim_step(const float* x, const float* __restrict__ eps,
                             const float* __restrict__ noise, float* out, size_t n,
                             const float* __restrict__ coef, const int32_t* __restrict__ step_dev, int clip) {
+  pdl_sync();
   const float* c = coef + 8 * (size_t)(*step_dev);
   const float s1 = c[0], sa = c[1], sp = c[2], cdir = c[3], sigma = c[4];
   size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -357,6 +359,7 @@ __global__ void k_ddim_step(const float* x, const float* __restrict__ eps,
 __global__ void k_ddpm_step(const float* x, const float* __restrict__ eps,
                             const float* __restrict__ noise, float* out, size_t n,
                             const float* __restrict__ coef, const int32_t* __restrict__ step_dev, int clip) {
+  pdl_sync();
   const float* c = coef + 8 * (size_t)(*step_dev);
   const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4];
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -369,10 +372,14 @@ __global__ void k_ddpm_step(const float* x, const float* __restrict__ eps,
   }
 }
 
-__global__ void k_advance_step(int32_t* step_dev, int advance) { *step_dev += advance; }
+__global__ void k_advance_step(int32_t* step_dev, int advance) {
+  pdl_sync();
+  *step_dev += advance;
+}
 
 __global__ void k_select_row(const float* __restrict__ table, int row_floats,
                              const int32_t* __restrict__ step_dev, float* __restrict__ dst, int reps) {
+  pdl_sync();
   const float* src = table + (size_t)(*step_dev) * row_floats;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_floats; i += gridDim.x * blockDim.x) {
     float v = src[i];
@@ -445,11 +452,11 @@ int advs_stem_im2col_ex(const float* x, void* col, int B, int H, int W, int Cin,
   __nv_bfloat16* c = (__nv_bfloat16*)col;
   const int parts = 18 * Cin <= 64 ? 2 : 1;
   if (Cin == 3) {
-    if (dtype == ADVS_F16) k_stem_im2col<3, true><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, 2);
-    else k_stem_im2col<3, false><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, 2);
+    if (dtype == ADVS_F16) launch_pdl(k_stem_im2col<3, true>, dim3(blocks), dim3(kStemPixPerBlock), 0, st, x, c, B, H, W, Cin, 2);
+    else launch_pdl(k_stem_im2col<3, false>, dim3(blocks), dim3(kStemPixPerBlock), 0, st, x, c, B, H, W, Cin, 2);
   } else {
-    if (dtype == ADVS_F16) k_stem_im2col<0, true><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, parts);
-    else k_stem_im2col<0, false><<<blocks, kStemPixPerBlock, 0, st>>>(x, c, B, H, W, Cin, parts);
+    if (dtype == ADVS_F16) launch_pdl(k_stem_im2col<0, true>, dim3(blocks), dim3(kStemPixPerBlock), 0, st, x, c, B, H, W, Cin, parts);
+    else launch_pdl(k_stem_im2col<0, false>, dim3(blocks), dim3(kStemPixPerBlock), 0, st, x, c, B, H, W, Cin, parts);
   }
   ADVS_CHECK_LAUNCH("stem_im2col");
   return ADVS_OK;
@@ -533,10 +540,10 @@ int advs_ddim_step(const float* x, const float* eps, const float* noise, float* 
   ADVS_CHECK_ARG(x && eps && out && coef && step_dev && n > 0, "ddim_step: bad args");
   ADVS_CHECK_ARG(((uintptr_t)x | (uintptr_t)eps | (uintptr_t)out | (uintptr_t)noise) % 16 == 0,
                  "ddim_step: pointers must be 16-byte aligned");
-  k_ddim_step<<<ew_blocks(n, 4), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, out, n, coef, step_dev, clip);
+  launch_pdl(k_ddim_step, dim3(ew_blocks(n, 4)), dim3(256), 0, (cudaStream_t)stream, x, eps, noise, out, n, coef, (const int32_t*)step_dev, clip);
   ADVS_CHECK_LAUNCH("ddim_step");
   if (advance) {
-    k_advance_step<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, advance);
+    launch_pdl(k_advance_step, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev, advance);
     ADVS_CHECK_LAUNCH("ddim_step/advance");
   }
   return ADVS_OK;
@@ -545,10 +552,10 @@ int advs_ddim_step(const float* x, const float* eps, const float* noise, float* 
 int advs_ddpm_step(const float* x, const float* eps, const float* noise, float* out, size_t n, const float* coef,
                    int32_t* step_dev, int advance, int clip, void* stream) {
   ADVS_CHECK_ARG(x && eps && out && coef && step_dev && n > 0, "ddpm_step: bad args");
-  k_ddpm_step<<<ew_blocks(n, 1), 256, 0, (cudaStream_t)stream>>>(x, eps, noise, out, n, coef, step_dev, clip);
+  launch_pdl(k_ddpm_step, dim3(ew_blocks(n, 1)), dim3(256), 0, (cudaStream_t)stream, x, eps, noise, out, n, coef, (const int32_t*)step_dev, clip);
   ADVS_CHECK_LAUNCH("ddpm_step");
   if (advance) {
-    k_advance_step<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, advance);
+    launch_pdl(k_advance_step, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev, advance);
     ADVS_CHECK_LAUNCH("ddpm_step/advance");
   }
   return ADVS_OK;
@@ -558,7 +565,7 @@ int advs_select_row(const float* table, int row_floats, const int32_t* step_dev,
   ADVS_CHECK_ARG(table && step_dev && dst && row_floats > 0 && reps > 0, "select_row: bad args");
   int blocks = (row_floats + 255) / 256;
   if (blocks > 148) blocks = 148;
-  k_select_row<<<blocks, 256, 0, (cudaStream_t)stream>>>(table, row_floats, step_dev, dst, reps);
+  launch_pdl(k_select_row, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, table, row_floats, step_dev, dst, reps);
   ADVS_CHECK_LAUNCH("select_row");
   return ADVS_OK;
 }

@@ -46,6 +46,7 @@ template <typename T>
 __global__ void k_gn_partial(const T* __restrict__ x, int C, int c_off, int Ctot, int HW, int pix_per_chunk,
                              float* __restrict__ part) {
   extern __shared__ float red[];  // [ppi][C]
+  pdl_sync();
   const int cv = C / 8;
   const int ppi = blockDim.x / cv;  // pixels per iteration (>= 1 by host check)
   const int pl = threadIdx.x / cv;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const float* __restrict__ p
                                                      int HW, float eps, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float* __restrict__ scale_shift) {
   __shared__ double red[2][4];
+  pdl_sync();
   const int b = blockIdx.x / groups, g = blockIdx.x % groups;
   const int Ctot = c0 + c1;
   const int cpg = Ctot / groups;
@@ -177,6 +179,7 @@ template <typename T, bool SILU, bool WIDE = false, bool OUT_F16 = false>
 __global__ void k_gn_apply(const T* __restrict__ x0, int c0, const T* __restrict__ x1, int c1, int HW,
                            int pix_per_chunk, const float* __restrict__ scale_shift, T* __restrict__ y,
                            const uint8_t* __restrict__ lo0 = nullptr, const uint8_t* __restrict__ lo1 = nullptr) {
+  pdl_sync();
   const int Ctot = c0 + c1;
   const int cv = Ctot / 8;
   const int ppi = blockDim.x / cv;
@@ -265,7 +268,7 @@ static int gn_partial_impl(const void* x, int C, int B, int HW, float* part, cud
   int ppi = threads / cv;
   size_t smem = (size_t)ppi * C * sizeof(float);
   dim3 grid(g.chunks, B);
-  k_gn_partial<T><<<grid, threads, smem, st>>>((const T*)x, C, 0, C, HW, g.pix_per_chunk, part);
+  launch_pdl(k_gn_partial<T>, grid, dim3(threads), smem, st, (const T*)x, C, 0, C, HW, g.pix_per_chunk, part);
   ADVS_CHECK_LAUNCH("groupnorm_partial");
   return ADVS_OK;
 }
@@ -273,8 +276,8 @@ static int gn_partial_impl(const void* x, int C, int B, int HW, float* part, cud
 static int gn_finalize_impl(const float* part0, int c0, int parts0, int gran0, const float* part1, int c1, int parts1,
                             int gran1, int B, int HW, int groups, float eps, const float* gamma, const float* beta,
                             float* scale_shift, cudaStream_t st) {
-  k_gn_finalize<<<B * groups, 128, 0, st>>>(part0, c0, parts0, gran0, part1, c1, parts1, gran1, groups, HW, eps, gamma,
-                                            beta, scale_shift);
+  launch_pdl(k_gn_finalize, dim3(B * groups), dim3(128), 0, st, part0, c0, parts0, gran0, part1, c1, parts1, gran1, groups, HW, eps,
+             gamma, beta, scale_shift);
   ADVS_CHECK_LAUNCH("groupnorm_finalize");
   return ADVS_OK;
 }
@@ -303,9 +306,11 @@ static int gn_apply_impl(const void* x0, int c0, const void* x1, int c1, int B, 
   int threads = cv <= 256 ? 256 : 1024;
   dim3 grid(g.chunks, B);
   if (silu)
-    k_gn_apply<T, true><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y);
+    launch_pdl(k_gn_apply<T, true, false, false>, grid, dim3(threads), 0, st, (const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk,
+               ss, (T*)y, (const uint8_t*)nullptr, (const uint8_t*)nullptr);
   else
-    k_gn_apply<T, false><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, ss, (T*)y);
+    launch_pdl(k_gn_apply<T, false, false, false>, grid, dim3(threads), 0, st, (const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk,
+               ss, (T*)y, (const uint8_t*)nullptr, (const uint8_t*)nullptr);
   ADVS_CHECK_LAUNCH("groupnorm_apply");
   return ADVS_OK;
 }
@@ -318,8 +323,8 @@ static int gn_apply_wide_impl(const void* x0, const void* lo0, int c0, const voi
   int threads = cv <= 256 ? 256 : 1024;
   dim3 grid(g.chunks, B);
   const bool wide = lo0 || lo1;
-#define ADVS_GN(S, W_, F) k_gn_apply<T, S, W_, F><<<grid, threads, 0, st>>>((const T*)x0, c0, (const T*)x1, c1, HW, g.pix_per_chunk, \
-                                                                        ss, (T*)y, (const uint8_t*)lo0, (const uint8_t*)lo1)
+#define ADVS_GN(S, W_, F) launch_pdl(k_gn_apply<T, S, W_, F>, grid, dim3(threads), 0, st, (const T*)x0, c0, (const T*)x1, c1, HW, \
+                                     g.pix_per_chunk, ss, (T*)y, (const uint8_t*)lo0, (const uint8_t*)lo1)
   if (silu) {
     if (wide) { if (out_f16) ADVS_GN(true, true, true); else ADVS_GN(true, true, false); }
     else { if (out_f16) ADVS_GN(true, false, true); else ADVS_GN(true, false, false); }

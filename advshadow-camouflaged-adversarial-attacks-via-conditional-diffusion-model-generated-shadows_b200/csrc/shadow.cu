@@ -92,6 +92,7 @@ __global__ void k_ddim_final_composite(const float* x, const float* __restrict__
                                        const float* __restrict__ img, const float* __restrict__ centers,
                                        const float* __restrict__ radii, const float* __restrict__ fmask, int Cm,
                                        float* __restrict__ out, int C, int H, int W) {
+  pdl_sync();
   const int b = blockIdx.y;
   const int wq = W / VEC;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +177,10 @@ __global__ void k_ddim_final_composite(const float* x, const float* __restrict__
   }
 }
 
-__global__ void k_advance_step_s(int32_t* step_dev, int advance) { *step_dev += advance; }
+__global__ void k_advance_step_s(int32_t* step_dev, int advance) {
+  pdl_sync();
+  *step_dev += advance;
+}
 
 static int launch_final_composite(const float* x, const float* eps, float* x_out, const float* coef, int32_t* step_dev,
                                   int advance, int clip, const float* img, const float* centers, const float* radii,
@@ -186,14 +190,14 @@ static int launch_final_composite(const float* x, const float* eps, float* x_out
                                    (uintptr_t)out) % 16) == 0;
   const int quads = H * (vec ? W / 4 : W);
   dim3 grid((quads + 127) / 128, B);
-#define ADVS_FC(V, BL) k_ddim_final_composite<V, BL><<<grid, 128, 0, st>>>(x, eps, x_out, coef, step_dev, clip, img, centers, \
-                                                                          radii, fmask, Cm, out, C, H, W)
+#define ADVS_FC(V, BL) launch_pdl(k_ddim_final_composite<V, BL>, grid, dim3(128), 0, st, x, eps, x_out, coef, (const int32_t*)step_dev, clip, \
+                                  img, centers, radii, fmask, Cm, out, C, H, W)
   if (vec) { if (blur) ADVS_FC(4, true); else ADVS_FC(4, false); }
   else { if (blur) ADVS_FC(1, true); else ADVS_FC(1, false); }
 #undef ADVS_FC
   ADVS_CHECK_LAUNCH(who);
   if (eps && advance) {
-    k_advance_step_s<<<1, 1, 0, st>>>(step_dev, advance);
+    launch_pdl(k_advance_step_s, dim3(1), dim3(1), 0, st, step_dev, advance);
     ADVS_CHECK_LAUNCH(who);
   }
   return ADVS_OK;
