@@ -48,6 +48,7 @@ SIGNATURES = {
     "advs_version": (C.c_int, []),
     "advs_last_error": (C.c_char_p, []),
     "advs_device_is_sm100": (C.c_int, []),
+    "advs_set_pdl": (C.c_int, [_i]),
     "advs_timestep_embedding": (C.c_int, [_vp, _i, _vp, _i, _vp, _vp]),
     "advs_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "advs_pack_conv_weight": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

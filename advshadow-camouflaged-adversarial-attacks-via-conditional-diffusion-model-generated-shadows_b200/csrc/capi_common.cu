@@ -44,9 +44,12 @@ int current_device_sms() {
   return n;
 }
 
+// -1: follow the environment (ADVS_PDL=1 turns it on; default off); 0 / 1: set by advs_set_pdl
+static std::atomic<int> g_pdl{-1};
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("ADVS_PDL"); return !e || atoi(e) != 0; }();
-  return on;
+  static const bool env_on = [] { const char* e = getenv("ADVS_PDL"); return e && atoi(e) != 0; }();
+  const int v = g_pdl.load(std::memory_order_relaxed);
+  return v < 0 ? env_on : v != 0;
 }
 
 int validate_conv(const advs_conv_params* p, const char* who) {
@@ -91,6 +94,8 @@ int validate_conv(const advs_conv_params* p, const char* who) {
 extern "C" {
 
 int advs_version(void) { return 100; }
+
+int advs_set_pdl(int on) { return advs::g_pdl.exchange(on < 0 ? -1 : (on ? 1 : 0)); }
 
 const char* advs_last_error(void) { return advs::g_err; }
 

@@ -45,7 +45,8 @@ int current_device_sms();          // multiProcessorCount of the current device 
 // launch_pdl() therefore executes pdl_wait() in every thread before its first global-memory access that could
 // depend on an earlier kernel, and pdl_launch_dependents() right after (one grid of look-ahead).  The gain is at
 // small batches, where a step is latency-bound (batch 1, 256x256: 4.2 ms per step for 335 kernels).
-// ADVS_PDL=0 launches plainly.
+// Off by default: advs_set_pdl(1) (ShadowSampler does that while it captures the graph of a batch <= 2 engine in a
+// single-process run) or ADVS_PDL=1 turn it on; launches are plain otherwise.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

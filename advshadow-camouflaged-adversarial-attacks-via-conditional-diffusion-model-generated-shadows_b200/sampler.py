@@ -32,7 +32,8 @@ def _st():
 class ShadowSampler:
     def __init__(self, model: UNetModelBase, diffusion, batch_size, image_size, ddim_timesteps=50,
                  ddim_discr_method="uniform", clip_denoised=True, precision=None, mask_channels=1, use_graph=True,
-                 streams=1, shadow_flavour="dm2", graph_scope="trajectory", engine_options=None, _instance=0, _buffers=None):
+                 streams=1, shadow_flavour="dm2", graph_scope="trajectory", engine_options=None, pdl="auto", _instance=0,
+                 _buffers=None):
         """`streams` > 1 splits the batch into that many independent sub-batches, each with its own engine and
         CUDA stream: the HBM-bound kernels of one sub-batch (GroupNorm apply, stem, ...) then overlap with the
         tensor-bound kernels of the other on the same SMs (they need no shared memory, the conv CTAs need it all).
@@ -41,7 +42,12 @@ class ShadowSampler:
         flavours differ only in the mask blur.
         `graph_scope`: "trajectory" (one CUDA graph holds all n steps and the composite) or "step" (one graph per
         step, replayed n times from the host; kept for comparison).
-        `engine_options`: keyword arguments for UNetModel.engine (wide_prenorm, gemm_operands, ...; A/B measurements)."""
+        `engine_options`: keyword arguments for UNetModel.engine (wide_prenorm, gemm_operands, ...; A/B measurements).
+        `pdl`: programmatic dependent launch between the ~335 kernels of a step (advs_set_pdl): True / False, or
+        "auto" = on for latency-bound engines (batch <= 2) in a single-process run.  Batch 1, 256x256, DDIM-50:
+        209.6 -> 197.5 ms; nothing to gain from batch 8 up.  Multi-process runs keep it off: the round-2 `bench.py`
+        runs on 2 and 4 GPUs -- the first to combine it with two sub-batch streams and NCCL traffic -- stalled until
+        the NCCL watchdog fired, and the GPU budget ended before the cause could be isolated."""
         if not isinstance(model, UNetModelBase):
             raise TypeError("ShadowSampler needs an advshadow_b200 UNetModel")
         if streams > 1 and (batch_size % streams or batch_size // streams < 1):
@@ -57,6 +63,9 @@ class ShadowSampler:
         self.graph_scope = graph_scope
         self.precision = precision
         self.engine_options = dict(engine_options or {})
+        import os
+        single = int(os.environ.get("WORLD_SIZE", "1") or "1") <= 1
+        self.pdl = (batch_size // max(streams, 1) <= 2 and single) if pdl == "auto" else bool(pdl)
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("ShadowSampler runs on CUDA only (no CPU path)")
@@ -83,7 +92,7 @@ class ShadowSampler:
                                                            ddim_discr_method, clip_denoised, precision, mask_channels,
                                                            use_graph, streams=1, shadow_flavour=shadow_flavour,
                                                            graph_scope=graph_scope, engine_options=engine_options,
-                                                           _instance=i + 1, _buffers=bufs))
+                                                           pdl=self.pdl, _instance=i + 1, _buffers=bufs))
                 torch.cuda.synchronize(self.device)
             self.eng = self.children[0].eng
             self.launches_per_trajectory = sum(c.launches_per_trajectory for c in self.children)
@@ -138,6 +147,13 @@ class ShadowSampler:
             self._one_step(i == self.n - 1)
 
     def _capture(self):
+        prev = capi.lib().advs_set_pdl(1 if self.pdl else 0)      # the captured graph keeps this setting
+        try:
+            self._capture_graphs()
+        finally:
+            capi.lib().advs_set_pdl(prev)
+
+    def _capture_graphs(self):
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -197,7 +213,11 @@ class ShadowSampler:
             return self.out
         self._sync_weights()
         if self.graph is None:
-            self._trajectory()
+            prev = capi.lib().advs_set_pdl(1 if self.pdl else 0)
+            try:
+                self._trajectory()
+            finally:
+                capi.lib().advs_set_pdl(prev)
         elif self.graph_scope == "trajectory":
             self.graph.replay()
         else:

@@ -342,9 +342,36 @@ def main():
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in (x_T, clean, fmask, cen, rad))
     d2h = out_host.numel() * 4
+    if world > 1:
+        # every collective of the run is behind us: leave the process group NOW, on all ranks together.  What follows
+        # is rank 0's per-kernel profiling (seconds of collective-free work); ranks that waited for it inside an NCCL
+        # barrier kept their GPUs spinning, and a stall there would also have swallowed the (then unflushed) JSON line.
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
     out = None
     if rank == 0:
+        # safety net: the timed numbers exist from here on.  If the (untimed) profiling / baseline legs below ever stall,
+        # print the line with what is known instead of losing the run.
+        done = threading.Event()
+
+        def fallback():
+            if not done.is_set():
+                print(json.dumps({
+                    "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload(args),
+                    "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                           "ms_per_step": ms_e2e / args.steps},
+                    "gpu_launches": sampler.launches_per_trajectory * args.steps + args.steps,
+                    "roofline": None, "note": "per-kernel profiling / baseline legs did not finish within 600 s; timed legs only"}),
+                    flush=True)
+                os._exit(0)
+
+        guard = threading.Timer(600.0, fallback)
+        guard.daemon = True
+        guard.start()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -414,10 +441,9 @@ def main():
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"1 image x 2 of {n} DDIM steps at {S}x{S} (oracle/torch_port.py, fp32), "
                                              f"{per_step:.2f} s/step, extrapolated x{n}"}
-        print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        done.set()
+        guard.cancel()
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,10 @@ int advs_version(void);
 const char* advs_last_error(void);
 /* 1 if the device behind the current context is compute capability 10.x */
 int advs_device_is_sm100(void);
+/* Programmatic dependent launch between the library's kernels (each kernel's prologue overlaps the previous
+ * kernel's tail; a captured CUDA graph keeps the setting it was captured with).  on: 1 / 0, or -1 = follow the
+ * environment (ADVS_PDL=1, default off).  Returns the previous setting.  Pays at batch 1-2 only. */
+int advs_set_pdl(int on);
 
 /* ---- K6: timestep embedding + small linears (dm1:16-33, dm1:184-188, dm1:77-80) ----------- */
 /* out[i, 0:half] = cos(t_i * f_j), out[i, half:2*half] = sin(t_i * f_j)  (dm1:25-30, "cos first").
