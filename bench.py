@@ -355,6 +355,7 @@ def main():
         # safety net: the timed numbers exist from here on.  If the (untimed) profiling / baseline legs below ever stall,
         # print the line with what is known instead of losing the run.
         done = threading.Event()
+        n_launches = sampler.launches_per_trajectory * args.steps + args.steps
 
         def fallback():
             if not done.is_set():
@@ -364,7 +365,7 @@ def main():
                     "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": workload(args),
                     "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                            "ms_per_step": ms_e2e / args.steps},
-                    "gpu_launches": sampler.launches_per_trajectory * args.steps + args.steps,
+                    "gpu_launches": n_launches,
                     "roofline": None, "note": "per-kernel profiling / baseline legs did not finish within 600 s; timed legs only"}),
                     flush=True)
                 os._exit(0)
@@ -414,7 +415,7 @@ def main():
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": sampler.launches_per_trajectory * args.steps + args.steps,
+            "gpu_launches": n_launches,
             "roofline": {"kernel": "k_conv_sm100_2cta[_halo] (tcgen05 cta_group::2 implicit-GEMM conv, all launches of one UNet forward)",
                          "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                          "achieved_min_median_max": [round(conv_tf[0], 1), round(ach, 1), round(conv_tf[-1], 1)] if conv_tf else None,
