@@ -202,7 +202,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // arithmetic.  Encoding is integer-only and cheaper than the plain bf16 conversion it replaces:
 //   u  = bits(v) + 0x8000          hi = u >> 16   (bf16 rounded to nearest, ties away from zero)
 //   lo = int8((u >> 8) & 0xFF) - 128 = byte 1 of u, sign bit flipped      (floor of the signed remainder / 256)
-// hi is also a GEMM operand and the residual for every other consumer; |v - decoded| < 2^-16 |v|.
+// hi is also a GEMM operand and the residual for every other consumer; 0 <= |v| - |decoded| < 2^-15 |v| (2^-16 on average).
 __device__ __forceinline__ uint32_t wide_round_bits(float v) { return __float_as_uint(v) + 0x8000u; }
 // two rounded bit patterns -> packed bf16x2 (their upper halves)
 __device__ __forceinline__ uint32_t wide_hi2(uint32_t u0, uint32_t u1) { return __byte_perm(u0, u1, 0x7632); }

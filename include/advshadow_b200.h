@@ -182,7 +182,7 @@ typedef struct advs_conv_params {
   /* optional (out_mode 0, ADVS_BF16): "wide" storage for a tensor that a GroupNorm will read.  y stays a
    * round-to-nearest bf16 tensor (ties away from zero; GEMM operand / residual for every other consumer);
    * y_lo[B,H,W,Cout] int8 holds the next 8 mantissa bits: value ~= as_float((bits(y) << 16) + ((int)y_lo << 8)),
-   * exact to 2^-16 relative.
+   * exact to 2^-15 relative (2^-16 on average).
    * advs_groupnorm_apply_wide reads the pair, so the normalised GEMM operand is rounded once instead of twice
    * (the reference normalises fp32 tensors, dm1:71-72, 83-84). */
   void* y_lo;

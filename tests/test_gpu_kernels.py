@@ -465,19 +465,7 @@ def test_upsample_conv_as_four_phase_convs(ops, case, gran):
 
 
 # ---- "wide" pre-norm storage: bf16 + int8 mantissa extension (advs_conv_params.y_lo) -------------------------
-def wide_decode(hi_bf16, lo_i8):
-    """value = as_float((bits(hi) << 16) + (lo << 8)) -- the decode rule stated in include/advshadow_b200.h"""
-    bits = (hi_bf16.view(torch.int16).to(torch.int32) << 16) + (lo_i8.to(torch.int32) << 8)
-    return bits.view(torch.float32)
-
-
-def wide_encode(x_f32):
-    """host restatement of the epilogue's encoder (csrc/common.cuh): u = bits(x) + 0x8000; hi = u >> 16 (bf16, nearest,
-    ties away from zero); lo = int8(byte 1 of u) - 128"""
-    u = x_f32.view(torch.int32) + 0x8000
-    hi = (u >> 16).to(torch.int16).view(torch.bfloat16)
-    lo = (((u >> 8) & 0xFF) - 128).to(torch.int8)
-    return hi, lo
+from wide_format import wide_decode, wide_encode  # noqa: E402  (tests/wide_format.py)
 
 
 WIDE_CASES = [

@@ -244,3 +244,35 @@ def test_no_cpu_fallback_and_error_surface(dm1_params):
     for n in ["os", "Dataset", "DataLoader", "Image", "transforms", "torch", "UNetModel", "GaussianDiffusion", "tqdm",
               "plt", "np", "F", "nn", "math"]:
         assert hasattr(dropin, n), n
+
+
+def test_wide_prenorm_format_properties():
+    """The bf16 + int8 mantissa-extension format (advs_conv_params.y_lo), restated with integer ops on the host:
+    decode(encode(x)) is within 2^-15 relative of x everywhere (2^-16 on average: the extension truncates) -- across
+    binade boundaries, for both signs, for values that round up into the next binade, for denormals and zero -- and
+    the bf16 part alone is the nearest bf16 (ties away from zero), i.e. what every other consumer of the tensor reads
+    is an ordinary correctly rounded bf16 tensor."""
+    from wide_format import wide_decode, wide_encode
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([
+        torch.randn(200000, generator=g) * 3,
+        torch.randn(50000, generator=g) * 1e-3,
+        (torch.rand(50000, generator=g) * 2 - 1) * 1e4,
+        torch.tensor([0.0, -0.0, 1.0, -1.0, 0.99999994, 1.9999999, -3.9999998, 2.0 ** -126, 1e-40, -1e-40, 65504.0, 3.3895314e38]),
+        # every exponent, mantissa just below / at / above the bf16 rounding boundary
+        (torch.arange(-120, 120).float().exp2()[:, None] * torch.tensor([1.0, 1.00390624, 1.00390625, 1.00390626, 1.9960937, 1.9999999])[None]).flatten(),
+    ])
+    hi, lo = wide_encode(x)
+    dec = wide_decode(hi, lo)
+    err = (dec.double() - x.double()).abs()
+    # (fp32 denormals: 256 denormal quanta = 3.6e-43 absolute -- there is no hidden bit to scale with)
+    assert bool((err <= torch.clamp(x.double().abs() * 2.0 ** -15, min=3.6e-43)).all())
+    assert float((err / x.double().abs().clamp_min(1e-30))[x.abs() > 1e-30].mean()) < 2.0 ** -16
+    assert bool((dec.abs() <= x.abs()).all()), "the extension truncates: the decoded magnitude never exceeds the value's"
+    # hi alone: nearest bf16 (torch rounds ties to even: the two may differ only on an exact tie)
+    rn = x.to(torch.bfloat16)
+    tie = (x.view(torch.int32) & 0xFFFF) == 0x8000
+    assert bool(((hi == rn) | tie | ~torch.isfinite(hi.float())).all()), "the bf16 part differs from round-to-nearest away from a tie"
+    # the extension never moves a value by more than half a bf16 ulp
+    fin = torch.isfinite(hi.float())
+    assert bool(((dec - hi.float()).abs()[fin] <= (torch.maximum(hi.float().abs(), dec.abs()) * 2.0 ** -8 + 1e-38)[fin]).all())
