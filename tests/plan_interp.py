@@ -41,7 +41,7 @@ def _sm100_ok(plan, a):
 def run_plan(plan, params, x, timesteps, round_bf16=False, wide_prenorm=2, gemm_operands="fp16", mixed_mma=False,
              exact_w=(), fp16_levels=2):
     """`wide_prenorm` (with round_bf16): conv outputs of that many top-resolution levels keep an unrounded copy that
-    only GroupNorm reads (the engine's bf16 + int8 mantissa-extension storage, exact to 2^-17).
+    only GroupNorm reads (the engine's bf16 + int8 mantissa-extension storage, exact to 2^-15 relative).
     `gemm_operands` = "fp16": GroupNorm outputs consumed by a tcgen05 conv, and the weights multiplying them, are
     rounded to fp16 instead of bf16 (engine.UNetEngine(gemm_operands=...)); `mixed_mma`: every other tcgen05
     conv's weights are fp16 as well (their activations stay bf16) -- the hardware rejects mixed operand formats

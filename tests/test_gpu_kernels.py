@@ -481,7 +481,7 @@ WIDE_CASES = [
 @pytest.mark.parametrize("impl", ["sm100", "simt"])
 @pytest.mark.parametrize("case", WIDE_CASES)
 def test_conv_wide_prenorm_storage(ops, impl, case):
-    """y stays the round-to-nearest bf16 tensor; (y, y_lo) together carry the fp32 accumulator to 2^-17."""
+    """y stays the round-to-nearest bf16 tensor; (y, y_lo) together carry the fp32 accumulator to 2^-15 (2^-16 on average)."""
     import ctypes as C
     from advshadow_b200 import _capi as capi
     B, H, W, cin, cout, taps, with_res = case
@@ -574,7 +574,7 @@ def test_groupnorm_apply_wide(ops, c0, c1, silu, lo_mask):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     xs = [torch.randn(B, H, W, c, device="cuda") * 3 + 1.5 for c in (c0, c1) if c]
     enc = [wide_encode(x) for x in xs]
-    # what each source encodes: fp32 to 2^-17 where the extension is passed, the bf16 value where it is not
+    # what each source encodes: fp32 to 2^-15 where the extension is passed, the bf16 value where it is not
     seen = [wide_decode(h, l) if use else h.float() for (h, l), use in zip(enc, lo_mask)]
     for x, (h, l) in zip(xs, enc):
         assert ((wide_decode(h, l) - x).abs() <= x.abs() * 2 ** -15).all()      # < 2^-16 by construction
