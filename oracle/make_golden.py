@@ -422,7 +422,58 @@ def iddm_ckpt_cases():
     return out
 
 
-MINTERS = dict(iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+def _signature(fn):
+    import inspect
+    return [(q.name, q.kind.name, None if q.default is inspect.Parameter.empty else repr(q.default))
+            for q in inspect.signature(fn).parameters.values()]
+
+
+def _star_imported_names(script, module):
+    """Names a script reads without binding them itself, that the star-imported module supplies."""
+    import ast
+    import builtins
+    tree = ast.parse(open(os.path.join(R.REF_ROOT, script)).read())
+    bound = set(dir(builtins))
+    for n in ast.walk(tree):
+        if isinstance(n, (ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)):
+            bound.add(n.name)
+        elif isinstance(n, ast.arg):
+            bound.add(n.arg)
+        elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+            bound.add(n.id)
+        elif isinstance(n, (ast.Import, ast.ImportFrom)):
+            bound.update((a.asname or a.name).split(".")[0] for a in n.names if a.name != "*")
+        elif isinstance(n, ast.ExceptHandler) and n.name:
+            bound.add(n.name)
+    used = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+    return sorted(u for u in used - bound if hasattr(module, u))
+
+
+def api_surface():
+    """The Python surface the drop-in modules must reproduce: every public name of the reference's
+    diff_model / ddim2/diff_model2 namespaces (what `from diff_model import *` hands to main.py:6 / main2.py:6), the
+    names those two scripts actually take from the star import, and the signatures (parameter names, order, defaults)
+    of UNetModel / GaussianDiffusion / PretrainedResNet50 methods and the module-level functions."""
+    import inspect
+    out = {}
+    for key, mod, script in (("dm1", R.dm1(), "main.py"), ("dm2", R.dm2(), "ddim2/main2.py")):
+        names = sorted(n for n in vars(mod) if not n.startswith("_"))
+        classes, functions = {}, {}
+        for n in names:
+            obj = getattr(mod, n)
+            if getattr(obj, "__module__", None) != mod.__name__:
+                continue
+            if inspect.isclass(obj):
+                classes[n] = {m: _signature(f) for m, f in vars(obj).items() if inspect.isfunction(f) and
+                              (not m.startswith("__") or m == "__init__")}
+            elif inspect.isfunction(obj):
+                functions[n] = _signature(obj)
+        out[key] = dict(names=names, classes=classes, functions=functions, script=script,
+                        star_names_used=_star_imported_names(script, mod))
+    return out
+
+
+MINTERS = dict(api_surface=api_surface, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

@@ -270,6 +270,51 @@ def test_no_cpu_fallback_and_error_surface(dm1_params):
         assert hasattr(dropin, n), n
 
 
+def test_dropin_modules_reproduce_the_reference_surface(golden):
+    """`dropin/diff_model.py` / `dropin/diff_model2.py` against the surface of the reference modules
+    recorded by oracle/make_golden.py::api_surface (names, classes, methods, parameter names / order / defaults).
+    Every name the reference scripts take from their star import (main.py:6, ddim2/main2.py:6) must be supplied; the
+    classes and functions on the sampling path must accept every call the reference's accept (same leading
+    parameters with the same defaults; additions are allowed only after them and only with defaults)."""
+    import importlib
+    import inspect
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "dropin"))
+    surf = golden("api_surface.pt")
+    # module building blocks that exist in the reference only as nn.Module internals: the engine executes the plan, the
+    # parameter holders are private (_model.py) -- nothing imports these names from the module (grep of the reference)
+    internal = {"AttentionBlock", "Downsample", "ResidualBlock", "TimestepBlock", "TimestepEmbedSequential", "Upsample"}
+    for key, modname in (("dm1", "diff_model"), ("dm2", "diff_model2")):
+        s, mod = surf[key], importlib.import_module(modname)
+        for n in s["star_names_used"]:
+            assert hasattr(mod, n), f"{s['script']} takes `{n}` from `from {modname} import *`"
+        missing = [n for n in s["names"] if not hasattr(mod, n) and n not in internal]
+        assert not missing, f"{modname}: {missing}"
+
+        def check(ours, want, what):
+            got = [(q.name, q.kind.name, None if q.default is inspect.Parameter.empty else repr(q.default))
+                   for q in inspect.signature(ours).parameters.values()]
+            got = [g for g in got if g[1] != "VAR_KEYWORD"]
+            for i, (name, kind, default) in enumerate(want):
+                # (a parameter the reference requires may have a default here: every reference call is still accepted)
+                assert i < len(got) and got[i][0] == name and (default is None or got[i][2] == default), \
+                    f"{what}: parameter {i} {got[i:i+1]} != {(name, default)}"
+                assert got[i][1] in (kind, "POSITIONAL_OR_KEYWORD"), what
+            for extra in got[len(want):]:
+                assert extra[2] is not None or extra[1] in ("VAR_POSITIONAL", "VAR_KEYWORD"), f"{what}: new required parameter {extra}"
+
+        for fn, want in s["functions"].items():
+            check(getattr(mod, fn), want, f"{modname}.{fn}")
+        for cls, methods in s["classes"].items():
+            if cls in internal:
+                continue
+            for m, want in methods.items():
+                assert hasattr(getattr(mod, cls), m), f"{modname}.{cls}.{m} missing"
+                check(getattr(getattr(mod, cls), m), want, f"{modname}.{cls}.{m}")
+    # the sampler the reference ships only in diff_model.py is also offered by the diff_model2 flavour (additive)
+    assert hasattr(importlib.import_module("diff_model2").GaussianDiffusion, "ddim_sample")
+
+
 def test_wide_prenorm_format_properties():
     """The bf16 + int8 mantissa-extension format (advs_conv_params.y_lo), restated with integer ops on the host:
     decode(encode(x)) is within 2^-15 relative of x everywhere (2^-16 on average: the extension truncates) -- across
