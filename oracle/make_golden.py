@@ -470,6 +470,15 @@ def api_surface():
                 functions[n] = _signature(obj)
         out[key] = dict(names=names, classes=classes, functions=functions, script=script,
                         star_names_used=_star_imported_names(script, mod))
+    # the IDDM generator: model/networks/unet.py:17-128, model/samples/ddim.py:25-100,
+    # utils/checkpoint.py:21-157
+    import importlib
+    UNet, DDIM = R.iddm()
+    ck = importlib.import_module("utils.checkpoint")
+    out["iddm"] = {"UNet.__init__": _signature(UNet.__init__), "UNet.forward": _signature(UNet.forward),
+                   "DDIMDiffusion.__init__": _signature(DDIM.__init__), "DDIMDiffusion.sample": _signature(DDIM.sample),
+                   "save_ckpt": _signature(ck.save_ckpt), "load_model_ckpt": _signature(ck.load_model_ckpt),
+                   "load_ckpt": _signature(ck.load_ckpt)}
     return out
 
 

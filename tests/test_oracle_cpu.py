@@ -284,24 +284,24 @@ def test_dropin_modules_reproduce_the_reference_surface(golden):
     # module building blocks that exist in the reference only as nn.Module internals: the engine executes the plan, the
     # parameter holders are private (_model.py) -- nothing imports these names from the module (grep of the reference)
     internal = {"AttentionBlock", "Downsample", "ResidualBlock", "TimestepBlock", "TimestepEmbedSequential", "Upsample"}
+
+    def check(ours, want, what):
+        got = [(q.name, q.kind.name, None if q.default is inspect.Parameter.empty else repr(q.default))
+               for q in inspect.signature(ours).parameters.values()]
+        for i, (name, kind, default) in enumerate(want):
+            # (a parameter the reference requires may have a default here: every reference call is still accepted)
+            assert i < len(got) and got[i][0] == name and (default is None or got[i][2] == default), \
+                f"{what}: parameter {i} {got[i:i+1]} != {(name, default)}"
+            assert got[i][1] in (kind, "POSITIONAL_OR_KEYWORD"), what
+        for extra in got[len(want):]:
+            assert extra[2] is not None or extra[1] in ("VAR_POSITIONAL", "VAR_KEYWORD"), f"{what}: new required parameter {extra}"
+
     for key, modname in (("dm1", "diff_model"), ("dm2", "diff_model2")):
         s, mod = surf[key], importlib.import_module(modname)
         for n in s["star_names_used"]:
             assert hasattr(mod, n), f"{s['script']} takes `{n}` from `from {modname} import *`"
         missing = [n for n in s["names"] if not hasattr(mod, n) and n not in internal]
         assert not missing, f"{modname}: {missing}"
-
-        def check(ours, want, what):
-            got = [(q.name, q.kind.name, None if q.default is inspect.Parameter.empty else repr(q.default))
-                   for q in inspect.signature(ours).parameters.values()]
-            got = [g for g in got if g[1] != "VAR_KEYWORD"]
-            for i, (name, kind, default) in enumerate(want):
-                # (a parameter the reference requires may have a default here: every reference call is still accepted)
-                assert i < len(got) and got[i][0] == name and (default is None or got[i][2] == default), \
-                    f"{what}: parameter {i} {got[i:i+1]} != {(name, default)}"
-                assert got[i][1] in (kind, "POSITIONAL_OR_KEYWORD"), what
-            for extra in got[len(want):]:
-                assert extra[2] is not None or extra[1] in ("VAR_POSITIONAL", "VAR_KEYWORD"), f"{what}: new required parameter {extra}"
 
         for fn, want in s["functions"].items():
             check(getattr(mod, fn), want, f"{modname}.{fn}")
@@ -311,6 +311,13 @@ def test_dropin_modules_reproduce_the_reference_surface(golden):
             for m, want in methods.items():
                 assert hasattr(getattr(mod, cls), m), f"{modname}.{cls}.{m} missing"
                 check(getattr(getattr(mod, cls), m), want, f"{modname}.{cls}.{m}")
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import iddm
+    for what, want in surf["iddm"].items():
+        obj = iddm
+        for part in what.split("."):
+            obj = getattr(obj, part)
+        check(obj, want, "iddm." + what)
     # the sampler the reference ships only in diff_model.py is also offered by the diff_model2 flavour (additive)
     assert hasattr(importlib.import_module("diff_model2").GaussianDiffusion, "ddim_sample")
 
