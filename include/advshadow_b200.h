@@ -14,7 +14,15 @@
  *   - no allocation, no synchronisation, no host callbacks inside any launch
  *     function: all of them are CUDA-graph capturable; scratch memory is
  *     supplied by the caller;
- *   - return value 0 = ok, <0 = error (advs_last_error() gives the text);
+ *   - return value 0 = ok, <0 = error (advs_last_error() gives the text; the message buffer is
+ *     thread-local, so it is the last error of the CALLING thread and stays valid until that thread's
+ *     next failing call);
+ *   - host threads: plans are immutable after *_plan returns and launches keep no host state, so
+ *     several threads may launch concurrently -- with one exception: the FIRST launch of each kernel
+ *     family on a device sets that kernel's shared-memory attribute; make it from one thread (a
+ *     warm-up call, which graph capture needs anyway) before launching the family from others.
+ *     Two launches on the same scratch / state buffers are the caller's to order, as with any
+ *     stream work;
  *   - activations are NHWC ("pixel-major"): element (b,h,w,c) of a [B,H,W,C]
  *     tensor lives at ((b*H+h)*W+w)*C+c.  Sampler state x_t / eps stay in the
  *     reference's NCHW fp32 layout;
