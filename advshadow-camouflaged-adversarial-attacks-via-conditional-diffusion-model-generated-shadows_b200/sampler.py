@@ -44,7 +44,7 @@ class ShadowSampler:
         step, replayed n times from the host; kept for comparison).
         `engine_options`: keyword arguments for UNetModel.engine (wide_prenorm, gemm_operands, ...; A/B measurements).
         `pdl`: programmatic dependent launch between the ~335 kernels of a step (advs_set_pdl): True / False, or
-        "auto" = on for latency-bound engines (batch <= 2) in a single-process run.  Batch 1, 256x256, DDIM-50:
+        "auto" = on for latency-bound engines (batch <= 2) in a single-process run (ADVS_PDL=0 / 1 overrides "auto").  Batch 1, 256x256, DDIM-50:
         209.6 -> 197.5 ms; nothing to gain from batch 8 up.  Multi-process runs keep it off: the round-2 `bench.py`
         runs on 2 and 4 GPUs -- the first to combine it with two sub-batch streams and NCCL traffic -- stalled until
         the NCCL watchdog fired, and the GPU budget ended before the cause could be isolated."""
@@ -65,7 +65,11 @@ class ShadowSampler:
         self.engine_options = dict(engine_options or {})
         import os
         single = int(os.environ.get("WORLD_SIZE", "1") or "1") <= 1
-        self.pdl = (batch_size // max(streams, 1) <= 2 and single) if pdl == "auto" else bool(pdl)
+        env = os.environ.get("ADVS_PDL", "")          # an explicit ADVS_PDL=0/1 overrides the "auto" heuristic
+        if pdl == "auto":
+            self.pdl = (env != "0") if env in ("0", "1") else (batch_size // max(streams, 1) <= 2 and single)
+        else:
+            self.pdl = bool(pdl)
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("ShadowSampler runs on CUDA only (no CPU path)")
