@@ -6,12 +6,13 @@ Public surface:
   ops                        tensor-level wrappers of single C-ABI entry points
   attack                     data-parallel attack-loop harness (success flags + ASR counts)
   datasets                   on-disk formats: image / mask_<name> / image_labels.json / id2label readers, writer
+  metrics                    evaluation metrics of the reference's scripts: FID, SSIM, PSNR (host side)
   iddm                       IDDM class-conditional UNet + CFG DDIM sampler (model/networks/unet.py, model/samples/ddim.py)
 The CUDA kernels live in csrc/ and are reached only through the C ABI in include/advshadow_b200.h.
 """
 from . import _capi  # noqa: F401
 
-__all__ = ["diff_model", "diff_model2", "shadow", "ops", "attack", "iddm", "datasets", "sampler", "plan", "engine"]
+__all__ = ["diff_model", "diff_model2", "shadow", "ops", "attack", "iddm", "datasets", "metrics", "sampler", "plan", "engine"]
 __version__ = "0.1.0"
 
 

@@ -422,6 +422,26 @@ def iddm_ckpt_cases():
     return out
 
 
+def metrics_cases():
+    """fid_fast.py:30-45 `calculate_fid`, taken from the reference SOURCE TEXT and executed unmodified (the script
+    itself downloads Inception weights and reads Windows paths at import), on recorded activation sets: a
+    well-conditioned pair, a shifted pair, and a rank-deficient pair (fewer samples than features: sqrtm turns
+    complex and the reference drops the imaginary part)."""
+    import ast
+    from scipy import linalg
+    src = open(os.path.join(R.REF_ROOT, "fid_fast.py")).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "calculate_fid"]
+    ns = {"np": np, "linalg": linalg}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), "fid_fast.py", "exec"), ns)
+    rng = np.random.RandomState(5)
+    cases = []
+    for n1, n2, d, shift in ((64, 80, 24, 0.0), (200, 200, 16, 0.7), (10, 12, 16, 0.1)):
+        a1 = rng.randn(n1, d).astype(np.float32) * (1 + rng.rand(d).astype(np.float32))
+        a2 = rng.randn(n2, d).astype(np.float32) * (1 + rng.rand(d).astype(np.float32)) + np.float32(shift)
+        cases.append(dict(act1=torch.from_numpy(a1), act2=torch.from_numpy(a2), fid=float(ns["calculate_fid"](a1, a2))))
+    return dict(fid=cases)
+
+
 def _signature(fn):
     import inspect
     return [(q.name, q.kind.name, None if q.default is inspect.Parameter.empty else repr(q.default))
@@ -482,7 +502,7 @@ def api_surface():
     return out
 
 
-MINTERS = dict(api_surface=api_surface, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+MINTERS = dict(api_surface=api_surface, metrics=metrics_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":
