@@ -46,8 +46,9 @@ class ShadowSampler:
         `pdl`: programmatic dependent launch between the ~335 kernels of a step (advs_set_pdl): True / False, or
         "auto" = on for latency-bound engines (batch <= 2) in a single-process run (ADVS_PDL=0 / 1 overrides "auto").  Batch 1, 256x256, DDIM-50:
         209.6 -> 197.5 ms; nothing to gain from batch 8 up.  Multi-process runs keep it off: the round-2 `bench.py`
-        runs on 2 and 4 GPUs -- the first to combine it with two sub-batch streams and NCCL traffic -- stalled until
-        the NCCL watchdog fired, and the GPU budget ended before the cause could be isolated."""
+        runs on 2 and 4 GPUs -- the first to combine it with two sub-batch streams and the NCCL exchange -- ended
+        after ~690 s without a result (what a 600 s collective time-out would look like), and the GPU budget ended
+        before the cause could be isolated."""
         if not isinstance(model, UNetModelBase):
             raise TypeError("ShadowSampler needs an advshadow_b200 UNetModel")
         if streams > 1 and (batch_size % streams or batch_size // streams < 1):
