@@ -422,6 +422,72 @@ def iddm_ckpt_cases():
     return out
 
 
+class _CheapEps(torch.nn.Module):
+    """A closed-form stand-in denoiser eps = a*x + b*(t/T) (elementwise, so bit-reproducible anywhere): lets the
+    reference's full sampling loops run in milliseconds for many schedule / discretisation settings."""
+
+    def __init__(self, T):
+        super().__init__()
+        self.T = T
+        self.dummy = torch.nn.Parameter(torch.zeros(1))      # ddim_sample / p_sample_loop ask for next(model.parameters())
+
+    def forward(self, x, t):
+        return x * 0.3 + (t.float() / self.T).view(-1, 1, 1, 1) * 0.05
+
+
+def sampler_loop_cases():
+    """The reference's complete ddim_sample (dm1:416-474) and sample (dm1:398-413) loops with a closed-form denoiser,
+    over the settings that shape the timestep tables and the per-step coefficients: both beta schedules, uniform and
+    quadratic discretisation, T % n != 0, eta > 0 (recorded noise draws), clip on / off.  Records the timesteps the
+    loop hands to the model and its output."""
+    dm1, dm2 = R.dm1(), R.dm2()
+    g = torch.Generator().manual_seed(21)
+    saved = dm1.torch
+
+    class Feed:
+        def __init__(self, tensors):
+            self.it = iter(tensors)
+
+        def __getattr__(self, k):
+            return getattr(saved, k)
+
+        def randn(self, *a, **k):
+            return next(self.it).clone()
+
+        def randn_like(self, x, *a, **k):
+            return next(self.it).clone()
+
+    ddim = []
+    for (sched, T, n, method, eta, clip) in [("cosine", 1000, 10, "uniform", 0.0, True), ("linear", 1000, 50, "uniform", 0.0, True),
+                                              ("linear", 1000, 30, "uniform", 0.0, True), ("cosine", 1000, 100, "uniform", 0.0, False),
+                                              ("linear", 1000, 20, "quad", 0.0, True), ("cosine", 1000, 50, "quad", 0.3, True),
+                                              ("linear", 500, 7, "uniform", 1.0, True), ("cosine", 200, 100, "uniform", 0.0, True)]:
+        gd = dm1.GaussianDiffusion(timesteps=T, beta_schedule=sched)
+        model, seen = _CheapEps(T), []
+        model.register_forward_pre_hook(lambda m, args: seen.append(args[1].clone()))
+        draws = [torch.randn(2, 3, 8, 8, generator=g) for _ in range(n + 1)]          # x_T, then one z per step
+        dm1.torch = Feed(draws)
+        try:
+            out = gd.ddim_sample(model, 8, batch_size=2, channels=3, ddim_timesteps=n, ddim_discr_method=method,
+                                 ddim_eta=eta, clip_denoised=clip)
+        finally:
+            dm1.torch = saved
+        ddim.append(dict(schedule=sched, T=T, n=n, method=method, eta=eta, clip=clip, x_T=draws[0], noise=torch.stack(draws[1:]),
+                         t=torch.stack(seen), out=torch.from_numpy(out)))
+    ddpm = []
+    for (sched, T) in [("cosine", 40), ("linear", 25)]:
+        gd = dm1.GaussianDiffusion(timesteps=T, beta_schedule=sched)
+        model = _CheapEps(T)
+        draws = [torch.randn(2, 3, 8, 8, generator=g) for _ in range(T + 1)]
+        dm1.torch = Feed(draws)
+        try:
+            imgs = gd.sample(model, 8, batch_size=2, channels=3)
+        finally:
+            dm1.torch = saved
+        ddpm.append(dict(schedule=sched, T=T, x_T=draws[0], noise=torch.stack(draws[1:]), traj=torch.from_numpy(np.stack(imgs))))
+    return dict(ddim=ddim, ddpm=ddpm, eps_a=0.3, eps_b=0.05)
+
+
 def metrics_cases():
     """fid_fast.py:30-45 `calculate_fid`, taken from the reference SOURCE TEXT and executed unmodified (the script
     itself downloads Inception weights and reads Windows paths at import), on recorded activation sets: a
@@ -502,7 +568,7 @@ def api_surface():
     return out
 
 
-MINTERS = dict(api_surface=api_surface, metrics=metrics_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+MINTERS = dict(api_surface=api_surface, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

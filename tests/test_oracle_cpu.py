@@ -352,3 +352,40 @@ def test_wide_prenorm_format_properties():
     # the extension never moves a value by more than half a bf16 ulp
     fin = torch.isfinite(hi.float())
     assert bool(((dec - hi.float()).abs()[fin] <= (torch.maximum(hi.float().abs(), dec.abs()) * 2.0 ** -8 + 1e-38)[fin]).all())
+
+
+def test_host_schedule_tables_reproduce_the_reference_loops(golden):
+    """Host half of the sampling loops against the reference's complete ddim_sample / sample runs with a closed-form
+    denoiser (tests/golden/sampler_loops.pt): the timestep tables (uniform / quadratic, T % n != 0), the per-step
+    coefficient rows (float64 tables -> gather -> fp32 -> fp32 math, both schedules, eta > 0, clip on / off) and the
+    DDPM posterior rows, pushed through the arithmetic k_ddim_step / k_ddpm_step perform (one rounding per operation,
+    csrc/elementwise.cu) -- bit-identical outputs.  The GPU tests check the kernels themselves against the same rule."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200.diff_model import GaussianDiffusion, ddim_timestep_tables
+    g = golden("sampler_loops.pt")
+    eps_of = lambda x, t, T: x * g["eps_a"] + (t.float() / T).view(-1, 1, 1, 1) * g["eps_b"]
+    for c in g["ddim"]:
+        gd = GaussianDiffusion(timesteps=c["T"], beta_schedule=c["schedule"])
+        seq, prev = ddim_timestep_tables(c["T"], c["n"], c["method"])
+        ts = [int(seq[i]) for i in reversed(range(c["n"]))]
+        assert ts == [int(t[0]) for t in c["t"]], (c["schedule"], c["T"], c["n"], c["method"])
+        coef = gd.ddim_coefficients(seq, prev, c["n"], c["eta"])
+        x = c["x_T"].clone()
+        for j, t in enumerate(ts):
+            s1, sa, sp, cdir, sigma = coef[j, :5]
+            e = eps_of(x, torch.full((x.shape[0],), t), c["T"])
+            x0 = (x - s1 * e) / sa
+            if c["clip"]:
+                x0 = x0.clamp(-1, 1)
+            x = (sp * x0 + cdir * e) + sigma * c["noise"][j]
+        assert torch.equal(x, c["out"]), (c["schedule"], c["T"], c["n"], c["method"], c["eta"])
+    for c in g["ddpm"]:
+        gd = GaussianDiffusion(timesteps=c["T"], beta_schedule=c["schedule"])
+        coef = gd.ddpm_coefficients()
+        x = c["x_T"].clone()
+        for j, t in enumerate(range(c["T"] - 1, -1, -1)):
+            c0, c1, c2, c3, c4 = coef[j, :5]
+            e = eps_of(x, torch.full((x.shape[0],), t), c["T"])
+            x0 = (c0 * x - c1 * e).clamp(-1, 1)
+            x = (c2 * x0 + c3 * x) + c4 * c["noise"][j]
+            assert torch.equal(x, c["traj"][j]), (c["schedule"], c["T"], t)
