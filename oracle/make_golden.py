@@ -485,7 +485,44 @@ def sampler_loop_cases():
         finally:
             dm1.torch = saved
         ddpm.append(dict(schedule=sched, T=T, x_T=draws[0], noise=torch.stack(draws[1:]), traj=torch.from_numpy(np.stack(imgs))))
-    return dict(ddim=ddim, ddpm=ddpm, eps_a=0.3, eps_b=0.05)
+    # IDDM DDIMDiffusion.sample (model/samples/ddim.py:48-100): fp32 linear schedule, (t, prev) pairs, classifier-free
+    # guidance through torch.lerp (both branches of its formula: |w| < 0.5 and >= 0.5), uint8 cast without clamp
+    _, DDIM = R.iddm()
+    ddim_mod = sys.modules["model.samples.ddim"]
+
+    class CheapCond(torch.nn.Module):
+        def __init__(self, T):
+            super().__init__()
+            self.T = T
+            self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, x, t, y=None):
+            e = x * 0.3 + (t.float() / self.T).view(-1, 1, 1, 1) * 0.05
+            return e if y is None else e + (y.float() + 1).view(-1, 1, 1, 1) * 0.02
+
+    iddm = []
+    real = ddim_mod.torch
+    for (T, n_steps, labelled, w) in [(1000, 50, False, None), (1000, 500, False, None), (1000, 20, True, 3.0), (1000, 20, True, 0.3),
+                                      (300, 7, True, 0.0)]:
+        diff = DDIM(noise_steps=T, sample_steps=n_steps, img_size=8, device="cpu")
+        x_T = torch.randn(3, 3, 8, 8, generator=g)
+        labels = torch.tensor([0, 4, 2]) if labelled else None
+
+        class FeedI:
+            def __getattr__(self, k):
+                return getattr(real, k)
+
+            def randn(self, *a, **k):
+                return x_T.clone()
+
+        ddim_mod.torch = FeedI()
+        try:
+            out = diff.sample(CheapCond(T), 3, labels, w)
+        finally:
+            ddim_mod.torch = real
+        iddm.append(dict(T=T, sample_steps=n_steps, labels=labels, cfg_scale=w, x_T=x_T, out=out,
+                         pairs=torch.tensor([[int(a), int(b)] for a, b in diff.time_step])))
+    return dict(ddim=ddim, ddpm=ddpm, iddm=iddm, eps_a=0.3, eps_b=0.05, eps_label=0.02)
 
 
 def metrics_cases():

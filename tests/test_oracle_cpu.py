@@ -389,3 +389,29 @@ def test_host_schedule_tables_reproduce_the_reference_loops(golden):
             x0 = (c0 * x - c1 * e).clamp(-1, 1)
             x = (c2 * x0 + c3 * x) + c4 * c["noise"][j]
             assert torch.equal(x, c["traj"][j]), (c["schedule"], c["T"], t)
+    # IDDM DDIMDiffusion.sample (model/samples/ddim.py:48-100): (t, prev) pairs, fp32 coefficient rows, classifier-free
+    # guidance as ATen's lerp formula (k_cfg_lerp), uint8 cast by truncation + wrap-around (k_to_uint8)
+    from advshadow_b200 import iddm
+
+    def lerp(start, end, w):          # k_cfg_lerp: |w| < 0.5 -> fma(w, end - start, start), else end - (end - start) * (1 - w)
+        d = end - start
+        if abs(w) < 0.5:
+            return (start.double() + float(torch.tensor(w, dtype=torch.float32)) * d.double()).float()
+        return end - d * (1 - torch.tensor(w, dtype=torch.float32))
+
+    for c in g["iddm"]:
+        diff = iddm.DDIMDiffusion(noise_steps=c["T"], sample_steps=c["sample_steps"], img_size=8, device="cpu")
+        assert [[int(a), int(b)] for a, b in diff.time_step] == c["pairs"].tolist()
+        coef = diff._coefficients()
+        x = c["x_T"].clone()
+        for j, (t, _) in enumerate(diff.time_step):
+            tt = torch.full((x.shape[0],), int(t))
+            e = eps_of(x, tt, c["T"])
+            if c["labels"] is not None:
+                cond = e + (c["labels"].float() + 1).view(-1, 1, 1, 1) * g["eps_label"]
+                e = lerp(e, cond, c["cfg_scale"]) if c["cfg_scale"] > 0 else cond
+            s1, sa, sp, cdir, sigma = coef[j, :5]
+            x0 = ((x - s1 * e) / sa).clamp(-1, 1)
+            x = sp * x0 + cdir * e
+        u8 = (((x + 1) * 0.5) * 255).to(torch.int64).to(torch.uint8)
+        assert torch.equal(u8, c["out"]), (c["T"], c["sample_steps"], c["cfg_scale"])
