@@ -38,6 +38,34 @@ def filenames_to_label_ids(filenames: Sequence[str], label_to_int: Dict[str, int
     return [label_to_int.get(label_from_filename(f), -1) for f in filenames]
 
 
+# ---- file-based evaluation (ASR_fast.py:90-126) ----
+def preprocess_image(image_path: str, size: int = 224) -> torch.Tensor:
+    """RGB -> Resize((224, 224)) -> ToTensor, no normalisation: [1,3,224,224] in [0,1] (ASR_fast.py:90-97)."""
+    from ._compat import Image, transforms
+    image = Image.open(image_path).convert('RGB')
+    return transforms.Compose([transforms.Resize((size, size)), transforms.ToTensor()])(image).unsqueeze(0)
+
+
+@torch.no_grad()
+def compute_asr(folder_path: str, model, int_to_label: Dict[int, str], device="cuda", batch_size: int = 64) -> float:
+    """Attack success rate of the images in a folder (ASR_fast.py:101-126): an image counts as a success when the
+    victim's argmax label differs from the text before the last '_' of its file name.  Same rule and preprocessing
+    as the reference, but the victim sees `batch_size` images per call and the decisions are taken on the GPU by
+    advs_success_flags.  `model`: any PyTorch classifier returning [N, classes] logits."""
+    import os
+    from . import ops
+    files = sorted(f for f in os.listdir(folder_path) if f.lower().endswith(('png', 'jpg', 'jpeg', 'bmp', 'gif')))
+    label_to_int = {v: k for k, v in int_to_label.items()}
+    ids = filenames_to_label_ids(files, label_to_int)
+    successes = total = 0
+    for lo in range(0, len(files), batch_size):
+        batch = torch.cat([preprocess_image(os.path.join(folder_path, f)) for f in files[lo:lo + batch_size]]).to(device)
+        logits = model(batch).float()
+        _, counts = ops.success_flags(logits, torch.tensor(ids[lo:lo + batch_size], device=logits.device))
+        successes, total = successes + int(counts[0]), total + int(counts[1])
+    return successes / total
+
+
 # ---- sharding ----
 def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous slice [lo, hi) of rank `rank`; the first n_items % world ranks get one extra item."""

@@ -422,6 +422,59 @@ def iddm_ckpt_cases():
     return out
 
 
+def asr_cases():
+    """ASR_fast.py:90-126 `preprocess_image` + `compute_asr`, taken from the reference SOURCE TEXT and executed
+    unmodified (the script itself loads fastai pickles from D:\\ at import) on a synthetic folder: lossless PNGs named
+    by the `<label>_<n>.<ext>` rule (incl. a label with underscores and one the id2label map does not know), a
+    non-image file, the reference's own config.json id2label map, a tiny seeded victim."""
+    import ast
+    import contextlib
+    import io
+    import json
+    import tempfile
+    from PIL import Image
+    from torchvision import transforms
+    src = open(os.path.join(R.REF_ROOT, "ASR_fast.py")).read()
+    fns = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in ("preprocess_image", "compute_asr")]
+    ns = {"os": os, "Image": Image, "transforms": transforms, "torch": torch, "device": torch.device("cpu")}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "ASR_fast.py", "exec"), ns)
+    id2label = json.load(open(os.path.join(R.REF_ROOT, "config.json")))["id2label"]
+    label_to_int = {label: int(i) for i, label in id2label.items()}                      # ASR_fast.py:71-75,99
+    int_to_label = {v: k for k, v in label_to_int.items()}
+    torch.manual_seed(4)
+    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 5, stride=4), torch.nn.Tanh(), torch.nn.AdaptiveAvgPool2d(3),
+                                 torch.nn.Flatten(), torch.nn.Linear(36, 37)).eval()
+    g = torch.Generator().manual_seed(8)
+    names = ["Abyssinian_1.png", "american_bulldog_12.png", "Bengal_3.png", "great_pyrenees_7.png", "Birman_2.png",
+             "not_a_pet_1.png", "Bombay_44.png", "yorkshire_terrier_5.png"]
+    pixels = [(torch.rand(40 + 7 * i, 50 + 3 * i, 3, generator=g) * 255).to(torch.uint8) for i in range(len(names))]
+    # make the victim right on some images: name them after what it predicts (through the same preprocessing)
+    seen = []
+    victim.register_forward_hook(lambda m, a, out: seen.append(out.detach().clone()))
+    with tempfile.TemporaryDirectory() as d, torch.no_grad():
+        for i, (n, px) in enumerate(zip(names, pixels)):
+            Image.fromarray(px.numpy()).save(os.path.join(d, n))
+        for i in (0, 2, 6):
+            pred = int(victim(ns["preprocess_image"](os.path.join(d, names[i]))).argmax(1))
+            new = f"{int_to_label[pred]}_{i}.png"
+            os.rename(os.path.join(d, names[i]), os.path.join(d, new))
+            names[i] = new
+        open(os.path.join(d, "notes.txt"), "w").write("not an image")
+        seen.clear()
+        order = [f for f in os.listdir(d) if f.lower().endswith(("png", "jpg", "jpeg", "bmp", "gif"))]
+        pre = {n: ns["preprocess_image"](os.path.join(d, n))[0] for n in names}
+        seen.clear()
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            asr = ns["compute_asr"](d, victim, int_to_label)
+        total, successes = [int(v) for v in buf.getvalue().split()]
+    logits = {n: l for n, l in zip(order, torch.cat(seen))}          # compute_asr walks os.listdir order
+    return dict(names=names, pixels=pixels, id2label=id2label, victim_state=victim.state_dict(),
+                logits=torch.stack([logits[n] for n in names]),
+                pre_probe=torch.stack([pre[n][:, ::16, ::16] for n in names]),
+                pre_sum=torch.stack([pre[n].double().sum() for n in names]), asr=asr, total=total, successes=successes)
+
+
 class _CheapEps(torch.nn.Module):
     """A closed-form stand-in denoiser eps = a*x + b*(t/T) (elementwise, so bit-reproducible anywhere): lets the
     reference's full sampling loops run in milliseconds for many schedule / discretisation settings."""
@@ -605,7 +658,7 @@ def api_surface():
     return out
 
 
-MINTERS = dict(api_surface=api_surface, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+MINTERS = dict(api_surface=api_surface, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

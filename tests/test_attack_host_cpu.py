@@ -84,3 +84,38 @@ def test_exchange_world_size_2_gloo(n_items):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_asr_rule_and_preprocessing_equal_reference_compute_asr(golden, tmp_path):
+    """SURVEY a17 against the reference's OWN compute_asr / preprocess_image (ASR_fast.py:90-126, executed from the
+    source text by oracle/make_golden.py::asr_cases): the same PNG files are written again, attack.preprocess_image
+    gives the reference's tensors, and the label plumbing (file-name rule, the reference's config.json id2label map,
+    unknown labels) turns the reference's logits into the reference's success count.  The GPU half of the rule
+    (advs_success_flags == torch.max) is tests/test_gpu_kernels.py's."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import attack
+    from PIL import Image
+    g = golden("asr.pt")
+    for n, px in zip(g["names"], g["pixels"]):
+        Image.fromarray(px.numpy()).save(str(tmp_path / n))
+    (tmp_path / "notes.txt").write_text("not an image")
+    pre = [attack.preprocess_image(str(tmp_path / n)) for n in g["names"]]
+    assert all(p.shape == (1, 3, 224, 224) for p in pre)
+    assert torch.equal(torch.stack([p[0][:, ::16, ::16] for p in pre]), g["pre_probe"])
+    assert torch.equal(torch.stack([p[0].double().sum() for p in pre]), g["pre_sum"])
+    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 5, stride=4), torch.nn.Tanh(), torch.nn.AdaptiveAvgPool2d(3),
+                                 torch.nn.Flatten(), torch.nn.Linear(36, 37)).eval()
+    victim.load_state_dict(g["victim_state"])
+    with torch.no_grad():
+        logits = victim(torch.cat(pre))
+    assert torch.allclose(logits, g["logits"], atol=1e-6)             # batched vs one image per call
+    cfg = tmp_path / "config.json"
+    cfg.write_text(json.dumps({"id2label": g["id2label"]}))
+    int_to_label, label_to_int = attack.load_id2label(str(cfg))
+    ids = torch.tensor(attack.filenames_to_label_ids(g["names"], label_to_int))
+    assert int(ids[g["names"].index("not_a_pet_1.png")]) == -1
+    flags = logits.argmax(1) != ids                                   # what advs_success_flags computes on the device
+    assert int(flags.sum()) == g["successes"] and len(g["names"]) == g["total"] == 8
+    assert int(flags.sum()) / len(g["names"]) == g["asr"]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        attack.compute_asr(str(tmp_path), victim, int_to_label, device="cpu")     # decisions are a GPU kernel: no CPU path
