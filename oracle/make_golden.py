@@ -422,6 +422,59 @@ def iddm_ckpt_cases():
     return out
 
 
+def dataset_cases():
+    """main.py:9-29 and ddim2/main2.py:30-66 `CustomDataset`, taken from the reference SOURCE TEXT and executed
+    unmodified on a synthetic folder: RGB PNGs, `mask_<name>` 0/255 'L' masks (mask_for_dataset.py:29,76-80), one
+    missing mask and one corrupt image (main2's loader moves on to the next index), the reference's
+    Resize + ToTensor transform (bilinear: mask edges come out soft), and the image_labels.json unpacking of
+    main.py:47-50."""
+    import ast
+    import contextlib
+    import io
+    import json
+    import tempfile
+    from PIL import Image, UnidentifiedImageError
+    from torch.utils.data import Dataset
+    from torchvision import transforms
+    classes = {}
+    for key, rel in (("main", "main.py"), ("main2", "ddim2/main2.py")):
+        tree = ast.parse(open(os.path.join(R.REF_ROOT, rel)).read())
+        body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CustomDataset"]
+        ns = {"Dataset": Dataset, "os": os, "Image": Image, "UnidentifiedImageError": UnidentifiedImageError}
+        exec(compile(ast.Module(body=body, type_ignores=[]), rel, "exec"), ns)
+        classes[key] = ns["CustomDataset"]
+    g = torch.Generator().manual_seed(12)
+    names = ["american_bulldog_12.png", "Abyssinian_3.png", "pug_1.png", "Bengal_9.png", "Birman_4.png"]
+    pixels = [(torch.rand(30 + 4 * i, 44 - 3 * i, 3, generator=g) * 255).to(torch.uint8) for i in range(len(names))]
+    masks = []
+    for px in pixels:
+        H, W = px.shape[:2]
+        yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        masks.append((((yy - H / 2) ** 2 + (xx - W / 3) ** 2) <= (H / 3) ** 2).to(torch.uint8) * 255)
+    labels_json = {n: n.rsplit("_", 1)[0] for n in names}
+    tf = transforms.Compose([transforms.Resize((32, 32)), transforms.ToTensor()])
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "images")), os.makedirs(os.path.join(d, "images_mask"))
+        for i, (n, px, m) in enumerate(zip(names, pixels, masks)):
+            if i == 3:
+                open(os.path.join(d, "images", n), "wb").write(b"this is not a PNG file")     # corrupt image
+            else:
+                Image.fromarray(px.numpy()).save(os.path.join(d, "images", n))
+            if i != 2:                                                                          # pug_1: mask missing
+                Image.fromarray(m.numpy()).save(os.path.join(d, "images_mask", "mask_" + n))
+        json.dump(labels_json, open(os.path.join(d, "image_labels.json"), "w"))
+        image_labels = json.load(open(os.path.join(d, "image_labels.json")))
+        files, labels = zip(*[(k, v) for k, v in image_labels.items()])                         # main.py:47-50
+        ds1 = classes["main"](os.path.join(d, "images"), files, labels, transform=tf)
+        ds2 = classes["main2"](os.path.join(d, "images"), os.path.join(d, "images_mask"), files, labels, transform=tf)
+        items1 = [ds1[i] for i in (0, 1, 2, 4)]                                                 # (index 3 raises: corrupt file)
+        with contextlib.redirect_stdout(io.StringIO()):
+            items2 = [ds2[i] for i in range(len(names))]
+    return dict(names=names, pixels=pixels, masks=masks, files=list(files), labels=list(labels), corrupt=3, no_mask=2,
+                main_items=[dict(image=a, label=b) for a, b in items1], main_index=[0, 1, 2, 4],
+                main2_items=[dict(image=a, mask=b, label=c) for a, b, c in items2], len=(len(ds1), len(ds2)))
+
+
 def asr_cases():
     """ASR_fast.py:90-126 `preprocess_image` + `compute_asr`, taken from the reference SOURCE TEXT and executed
     unmodified (the script itself loads fastai pickles from D:\\ at import) on a synthetic folder: lossless PNGs named
@@ -658,7 +711,7 @@ def api_surface():
     return out
 
 
-MINTERS = dict(api_surface=api_surface, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+MINTERS = dict(api_surface=api_surface, datasets=dataset_cases, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

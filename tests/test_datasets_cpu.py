@@ -93,3 +93,40 @@ def test_iddm_checkpoint_dict_matches_reference(golden, tmp_path):
     assert all(torch.equal(a, b) for a, b in zip(tgt.state_dict().values(), src.state_dict().values()))
     opt2 = torch.optim.SGD(toy(5).parameters(), lr=0.1, momentum=0.9)
     assert iddm.load_ckpt(str(tmp_path / "ckpt_last.pt"), toy(5), "cpu", optimizer=opt2, is_train=True) == 8
+
+
+def test_datasets_equal_the_reference_loaders(golden, tmp_path):
+    """datasets.ImageLabelDataset / ImageMaskLabelDataset against the reference's OWN `CustomDataset` classes
+    (main.py:9-29, ddim2/main2.py:30-66, executed from the source text by oracle/make_golden.py::dataset_cases) on the
+    same files: tensors bit-identical, labels identical, the sample with the missing mask and the corrupt image are
+    skipped to the same successor, image_labels.json unpacks to the same lists."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import datasets as D
+    from PIL import Image
+    from torchvision import transforms
+    g = golden("datasets.pt")
+    img_dir, mask_dir = tmp_path / "images", tmp_path / "images_mask"
+    img_dir.mkdir(), mask_dir.mkdir()
+    for i, (n, px, m) in enumerate(zip(g["names"], g["pixels"], g["masks"])):
+        if i == g["corrupt"]:
+            (img_dir / n).write_bytes(b"this is not a PNG file")
+        else:
+            Image.fromarray(px.numpy()).save(str(img_dir / n))
+        if i != g["no_mask"]:
+            Image.fromarray(m.numpy()).save(str(mask_dir / D.mask_name(n)))
+    (tmp_path / "image_labels.json").write_text(json.dumps({n: D.label_from_filename(n) for n in g["names"]}))
+    files, labels = D.load_image_labels(str(tmp_path / "image_labels.json"))
+    assert files == g["files"] and labels == g["labels"]
+    tf = transforms.Compose([transforms.Resize((32, 32)), transforms.ToTensor()])
+    ds1 = D.ImageLabelDataset(str(img_dir), files, labels, transform=tf)
+    ds2 = D.ImageMaskLabelDataset(str(img_dir), str(mask_dir), files, labels, transform=tf)
+    assert (len(ds1), len(ds2)) == tuple(g["len"])
+    for idx, want in zip(g["main_index"], g["main_items"]):
+        img, lab = ds1[idx]
+        assert torch.equal(img, want["image"]) and lab == want["label"]
+    with pytest.raises(OSError):
+        ds1[g["corrupt"]]                       # main.py's loader does not skip: PIL's error surfaces, as in the reference
+    for idx, want in enumerate(g["main2_items"]):
+        img, mask, lab = ds2[idx]
+        assert torch.equal(img, want["image"]) and torch.equal(mask, want["mask"]) and lab == want["label"], idx
+    assert ds2[g["no_mask"]][2] == ds2[g["corrupt"]][2] == g["labels"][4]     # both fall through to the last sample
