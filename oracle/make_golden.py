@@ -422,6 +422,48 @@ def iddm_ckpt_cases():
     return out
 
 
+def diffusion_helper_cases():
+    """The small tensor helpers of GaussianDiffusion (dm1:334-395, 475-484; dm2:656-680) on seeded inputs, for both
+    module flavours (cosine / linear default schedule): _extract, q_sample, q_mean_variance,
+    q_posterior_mean_variance, predict_start_from_noise, p_mean_variance, p_sample and train_losses with the
+    closed-form denoiser; the reference's randn_like draws are replaced by a recorded tensor."""
+    out = {}
+    g = torch.Generator().manual_seed(33)
+    x0 = torch.rand(4, 3, 8, 8, generator=g) * 2 - 1
+    xt = torch.randn(4, 3, 8, 8, generator=g)
+    z = torch.randn(4, 3, 8, 8, generator=g)
+    t = torch.tensor([0, 1, 500, 999])
+    for key, mod in (("dm1", R.dm1()), ("dm2", R.dm2())):
+        gd = mod.GaussianDiffusion(timesteps=1000)
+        model = _CheapEps(1000)
+        saved = mod.torch
+
+        class Feed:
+            def __getattr__(self, k):
+                return getattr(saved, k)
+
+            def randn_like(self, x, *a, **k):
+                return z.clone()
+
+        mod.torch = Feed()
+        try:
+            with torch.no_grad():
+                c = dict(extract=gd._extract(gd.sqrt_recip_alphas_cumprod, t, x0.shape),
+                         q_sample=gd.q_sample(x0, t, noise=z), q_sample_drawn=gd.q_sample(x0, t),
+                         q_mean_variance=gd.q_mean_variance(x0, t),
+                         q_posterior_mean_variance=gd.q_posterior_mean_variance(x0, xt, t),
+                         predict_start_from_noise=gd.predict_start_from_noise(xt, t, z),
+                         p_mean_variance=gd.p_mean_variance(model, xt, t),
+                         p_mean_variance_noclip=gd.p_mean_variance(model, xt, t, clip_denoised=False),
+                         p_sample=gd.p_sample(model, xt, t),
+                         train_losses=(gd.train_losses(model, x0, t) if key == "dm1" else gd.train_losses(model, x0, t, "cpu")))
+        finally:
+            mod.torch = saved
+        out[key] = c
+    out.update(x0=x0, xt=xt, z=z, t=t, eps_a=0.3, eps_b=0.05)
+    return out
+
+
 def dataset_cases():
     """main.py:9-29 and ddim2/main2.py:30-66 `CustomDataset`, taken from the reference SOURCE TEXT and executed
     unmodified on a synthetic folder: RGB PNGs, `mask_<name>` 0/255 'L' masks (mask_for_dataset.py:29,76-80), one
@@ -711,7 +753,7 @@ def api_surface():
     return out
 
 
-MINTERS = dict(api_surface=api_surface, datasets=dataset_cases, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+MINTERS = dict(api_surface=api_surface, diffusion_helpers=diffusion_helper_cases, datasets=dataset_cases, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

@@ -415,3 +415,34 @@ def test_host_schedule_tables_reproduce_the_reference_loops(golden):
             x = sp * x0 + cdir * e
         u8 = (((x + 1) * 0.5) * 255).to(torch.int64).to(torch.uint8)
         assert torch.equal(u8, c["out"]), (c["T"], c["sample_steps"], c["cfg_scale"])
+
+
+def test_diffusion_helpers_equal_reference(golden, monkeypatch):
+    """The tensor helpers of GaussianDiffusion that sit beside the sampling loop (dm1:334-395, 475-484; dm2:656-680)
+    against the reference's own outputs for both module flavours (tests/golden/diffusion_helpers.pt) -- plain host
+    torch code, so it is checked where it runs; the denoiser is the golden's closed-form stand-in."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import diff_model, diff_model2
+    g = golden("diffusion_helpers.pt")
+    x0, xt, z, t = g["x0"], g["xt"], g["z"], g["t"]
+    model = lambda x, tt: x * g["eps_a"] + (tt.float() / 1000).view(-1, 1, 1, 1) * g["eps_b"]
+    monkeypatch.setattr(torch, "randn_like", lambda x, *a, **k: z.clone())
+
+    def same(a, b):
+        if isinstance(b, (tuple, list)):
+            return len(a) == len(b) and all(same(u, v) for u, v in zip(a, b))
+        return torch.equal(a, b)
+
+    for key, mod in (("dm1", diff_model), ("dm2", diff_model2)):
+        gd, c = mod.GaussianDiffusion(timesteps=1000), g[key]
+        with torch.no_grad():
+            assert same(gd._extract(gd.sqrt_recip_alphas_cumprod, t, x0.shape), c["extract"])
+            assert same(gd.q_sample(x0, t, noise=z), c["q_sample"]) and same(gd.q_sample(x0, t), c["q_sample_drawn"])
+            assert same(gd.q_mean_variance(x0, t), c["q_mean_variance"])
+            assert same(gd.q_posterior_mean_variance(x0, xt, t), c["q_posterior_mean_variance"])
+            assert same(gd.predict_start_from_noise(xt, t, z), c["predict_start_from_noise"])
+            assert same(gd.p_mean_variance(model, xt, t), c["p_mean_variance"])
+            assert same(gd.p_mean_variance(model, xt, t, clip_denoised=False), c["p_mean_variance_noclip"])
+            assert same(gd.p_sample(model, xt, t), c["p_sample"])
+            loss = gd.train_losses(model, x0, t) if key == "dm1" else gd.train_losses(model, x0, t, "cpu")
+            assert same(loss, c["train_losses"])
