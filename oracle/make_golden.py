@@ -422,6 +422,30 @@ def iddm_ckpt_cases():
     return out
 
 
+def state_dict_layouts():
+    """state_dict key names, shapes and dtypes of the reference networks (what `model.load_state_dict(torch.load(p))`
+    at main.py:115 / gen.py:557 and the IDDM checkpoint loader rely on), per configuration, plus the sum of |w| after
+    `torch.manual_seed(0)` construction (same RNG consumption order => same initial weights)."""
+    dm1, dm2 = R.dm1(), R.dm2()
+    UNet, _ = R.iddm()
+    out = {}
+
+    def layout(make):
+        torch.manual_seed(0)
+        m = make()
+        return dict(entries=[(k, tuple(v.shape), str(v.dtype)) for k, v in m.state_dict().items()],
+                    checksum=float(sum(v.double().abs().sum() for v in m.state_dict().values() if v.is_floating_point())))
+
+    out["dm1_default"] = layout(lambda: dm1.UNetModel())
+    out["dm1_main"] = layout(lambda: dm1.UNetModel(channel_mult=(1, 2, 2, 2), attention_resolutions=(2,), dropout=0.1))
+    out["dm1_small"] = layout(lambda: dm1.UNetModel(model_channels=64, num_res_blocks=1, channel_mult=(1, 2), num_heads=2,
+                                                    attention_resolutions=(1, 2)))
+    out["dm2_default"] = layout(lambda: dm2.UNetModel())
+    out["iddm_cond64"] = layout(lambda: UNet(num_classes=10, image_size=64, device="cpu"))
+    out["iddm_uncond32_gelu"] = layout(lambda: UNet(image_size=32, device="cpu", act="gelu"))
+    return out
+
+
 def diffusion_helper_cases():
     """The small tensor helpers of GaussianDiffusion (dm1:334-395, 475-484; dm2:656-680) on seeded inputs, for both
     module flavours (cosine / linear default schedule): _extract, q_sample, q_mean_variance,
@@ -753,7 +777,7 @@ def api_surface():
     return out
 
 
-MINTERS = dict(api_surface=api_surface, diffusion_helpers=diffusion_helper_cases, datasets=dataset_cases, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
+MINTERS = dict(api_surface=api_surface, state_dicts=state_dict_layouts, diffusion_helpers=diffusion_helper_cases, datasets=dataset_cases, asr=asr_cases, metrics=metrics_cases, sampler_loops=sampler_loop_cases, iddm_ckpt=iddm_ckpt_cases, config1=config1, forwards=forwards, shadow=shadow_cases, schedules=schedules, stochastic=stochastic_cases,
                iddm=iddm_cases, dm2_256=dm2_256, shadow_blur=shadow_blur_cases, shadow_opt=shadow_opt_cases)
 
 if __name__ == "__main__":

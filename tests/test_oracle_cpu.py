@@ -446,3 +446,29 @@ def test_diffusion_helpers_equal_reference(golden, monkeypatch):
             assert same(gd.p_sample(model, xt, t), c["p_sample"])
             loss = gd.train_losses(model, x0, t) if key == "dm1" else gd.train_losses(model, x0, t, "cpu")
             assert same(loss, c["train_losses"])
+
+
+def test_state_dict_layouts_equal_reference(golden):
+    """Checkpoint interoperability (main.py:115 `model.load_state_dict(torch.load(path))`, the IDDM checkpoint loader):
+    every network flavour exposes the reference's state_dict -- same key names in the same order, same shapes and
+    dtypes -- and `torch.manual_seed(0)` construction yields the same initial weights (checksum)."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import diff_model, diff_model2, iddm
+    g = golden("state_dicts.pt")
+    makers = {
+        "dm1_default": lambda: diff_model.UNetModel(),
+        "dm1_main": lambda: diff_model.UNetModel(channel_mult=(1, 2, 2, 2), attention_resolutions=(2,), dropout=0.1),
+        "dm1_small": lambda: diff_model.UNetModel(model_channels=64, num_res_blocks=1, channel_mult=(1, 2), num_heads=2,
+                                                  attention_resolutions=(1, 2)),
+        "dm2_default": lambda: diff_model2.UNetModel(),
+        "iddm_cond64": lambda: iddm.UNet(num_classes=10, image_size=64, device="cpu"),
+        "iddm_uncond32_gelu": lambda: iddm.UNet(image_size=32, device="cpu", act="gelu"),
+    }
+    assert set(makers) == set(g)
+    for name, make in makers.items():
+        torch.manual_seed(0)
+        sd = make().state_dict()
+        got = [(k, tuple(v.shape), str(v.dtype)) for k, v in sd.items()]
+        assert got == [tuple(e) for e in g[name]["entries"]], name
+        chk = float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+        assert abs(chk - g[name]["checksum"]) <= 1e-9 * chk, name
