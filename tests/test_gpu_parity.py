@@ -647,3 +647,22 @@ def test_shadow_optimisation_matches_reference_golden(pkg, golden):
     cb, rb, ob = gd.optimize_shadow_position_batched(Victim, imgs, masks, labels, "cuda", iterations=g["iterations"])
     for i, c in enumerate(g["cases"]):
         check(cb[i], rb[i], ob[i], c, f"batched image {i}")
+
+
+def test_compute_asr_equals_reference_function(pkg, golden, tmp_path):
+    """attack.compute_asr (batched victim call, decisions by advs_success_flags) on the files of tests/golden/asr.pt
+    gives the ASR the reference's own compute_asr (ASR_fast.py:101-126) printed for them; the top-2 logit margins of
+    that golden are >= 4.8e-2, far above any fp32 / TF32 difference between the CPU and GPU victim."""
+    from PIL import Image
+    from advshadow_b200 import attack
+    g = golden("asr.pt")
+    for n, px in zip(g["names"], g["pixels"]):
+        Image.fromarray(px.numpy()).save(str(tmp_path / n))
+    (tmp_path / "notes.txt").write_text("not an image")
+    victim = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 5, stride=4), torch.nn.Tanh(), torch.nn.AdaptiveAvgPool2d(3),
+                                 torch.nn.Flatten(), torch.nn.Linear(36, 37)).eval()
+    victim.load_state_dict(g["victim_state"])
+    victim.cuda()
+    int_to_label = {int(i): l for i, l in g["id2label"].items()}
+    assert attack.compute_asr(str(tmp_path), victim, int_to_label, batch_size=3) == g["asr"]     # ragged last batch
+    assert attack.compute_asr(str(tmp_path), victim, int_to_label) == g["successes"] / g["total"]
