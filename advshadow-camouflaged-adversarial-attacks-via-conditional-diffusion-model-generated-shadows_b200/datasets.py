@@ -5,6 +5,9 @@ scripts read and write.  Host-side I/O only (PIL + JSON); nothing here touches t
   masks/mask_<image file name>              single-channel 0/255 PNG feature mask (mask_for_dataset.py:29,76-80)
   image_labels.json                         {"<file>": "<class name>", ...} (classifer_model.py:36-60, main.py:43-50)
   config*.json                              {"id2label": {"0": "Abyssinian", ...}} per victim (ASR_fast.py:67-75)
+  <generate_name>.<fmt>, <generate_name>_<i>.<fmt>   the IDDM generator's outputs: one grid image of the batch and one
+                                            file per sample, from uint8 [N,3,S,S] tensors (utils/utils.py:51-89,
+                                            tools/generate.py:79-80)
 """
 import json
 import os
@@ -85,3 +88,28 @@ def save_images(images, folder: str, names: Sequence[str]):
     arr = (images.detach().float().clamp(0, 1).mul(255).round().byte().permute(0, 2, 3, 1).cpu().numpy())
     for a, n in zip(arr, names):
         Image.fromarray(np.ascontiguousarray(a)).save(os.path.join(folder, n))
+
+
+def save_image_grid(images, path: str, **kwargs):
+    """uint8 [N,3,H,W] sampler output -> one grid image (torchvision.utils.make_grid defaults: 8 per row, 2-pixel
+    padding) written to `path` (utils/utils.py:51-62)."""
+    import numpy as np
+    import torchvision
+    grid = torchvision.utils.make_grid(tensor=images.cpu(), **kwargs)
+    Image.fromarray(np.ascontiguousarray(grid.permute(1, 2, 0).numpy())).save(path)
+
+
+def save_one_image_in_images(images, path: str, generate_name: str, image_size=None, image_format: str = "jpg", **kwargs):
+    """uint8 [N,3,H,W] -> `<generate_name>_<i>.<fmt>` per sample, plus `<generate_name>_<size>_<i>.<fmt>` resized
+    copies when `image_size` is given (utils/utils.py:65-89; the reference asks Pillow for `Image.ANTIALIAS`, which
+    current Pillow spells LANCZOS -- same filter)."""
+    import numpy as np
+    import torchvision
+    os.makedirs(path, exist_ok=True)
+    for count, one in enumerate(images.cpu()):
+        grid = torchvision.utils.make_grid(tensor=one, **kwargs)
+        im = Image.fromarray(np.ascontiguousarray(grid.permute(1, 2, 0).numpy()))
+        im.save(os.path.join(path, f"{generate_name}_{count}.{image_format}"))
+        if image_size is not None:
+            im.resize(size=(image_size, image_size), resample=getattr(Image, "LANCZOS", 1)).save(
+                os.path.join(path, f"{generate_name}_{image_size}_{count}.{image_format}"))

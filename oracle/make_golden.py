@@ -536,7 +536,22 @@ def dataset_cases():
         items1 = [ds1[i] for i in (0, 1, 2, 4)]                                                 # (index 3 raises: corrupt file)
         with contextlib.redirect_stdout(io.StringIO()):
             items2 = [ds2[i] for i in range(len(names))]
-    return dict(names=names, pixels=pixels, masks=masks, files=list(files), labels=list(labels), corrupt=3, no_mask=2,
+    # the IDDM generator's writers (utils/utils.py:51-89), from the source text, on a uint8 batch; read back as pixels
+    import logging
+    import torchvision
+    tree = ast.parse(open(os.path.join(R.REF_ROOT, "utils/utils.py")).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("save_images", "save_one_image_in_images")]
+    ns = {"torchvision": torchvision, "Image": Image, "os": os, "logger": logging.getLogger("ref")}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "utils/utils.py", "exec"), ns)
+    batch = (torch.rand(11, 3, 16, 16, generator=g) * 255).to(torch.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        ns["save_images"](images=batch, path=os.path.join(d, "df.png"))
+        ns["save_one_image_in_images"](images=batch, path=d, generate_name="df", image_format="png")
+        written = sorted(os.listdir(d))
+        grid = torch.from_numpy(np.array(Image.open(os.path.join(d, "df.png"))))
+        singles = torch.stack([torch.from_numpy(np.array(Image.open(os.path.join(d, f"df_{i}.png")))) for i in range(len(batch))])
+    writers = dict(batch=batch, written=written, grid=grid, singles=singles)
+    return dict(names=names, pixels=pixels, masks=masks, files=list(files), labels=list(labels), corrupt=3, no_mask=2, writers=writers,
                 main_items=[dict(image=a, label=b) for a, b in items1], main_index=[0, 1, 2, 4],
                 main2_items=[dict(image=a, mask=b, label=c) for a, b, c in items2], len=(len(ds1), len(ds2)))
 

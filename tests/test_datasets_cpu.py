@@ -130,3 +130,22 @@ def test_datasets_equal_the_reference_loaders(golden, tmp_path):
         img, mask, lab = ds2[idx]
         assert torch.equal(img, want["image"]) and torch.equal(mask, want["mask"]) and lab == want["label"], idx
     assert ds2[g["no_mask"]][2] == ds2[g["corrupt"]][2] == g["labels"][4]     # both fall through to the last sample
+
+
+def test_iddm_image_writers_equal_reference(golden, tmp_path):
+    """The IDDM generator's output files (utils/utils.py:51-89 via tools/generate.py:79-80): one grid image and one
+    file per sample from the uint8 batch -- same file names and, decoded, the same pixels as the reference's own
+    functions wrote (tests/golden/datasets.pt['writers']); the resized copies carry the size in their name."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import datasets as D
+    from PIL import Image
+    w = golden("datasets.pt")["writers"]
+    D.save_image_grid(w["batch"], str(tmp_path / "df.png"))
+    D.save_one_image_in_images(w["batch"], str(tmp_path), "df", image_format="png")
+    assert sorted(os.listdir(tmp_path)) == w["written"]
+    assert torch.equal(torch.from_numpy(np.array(Image.open(tmp_path / "df.png"))), w["grid"])
+    got = torch.stack([torch.from_numpy(np.array(Image.open(tmp_path / f"df_{i}.png"))) for i in range(len(w["batch"]))])
+    assert torch.equal(got, w["singles"]) and torch.equal(got, w["batch"].permute(0, 2, 3, 1))
+    D.save_one_image_in_images(w["batch"][:2], str(tmp_path / "big"), "df", image_size=32, image_format="png")
+    assert sorted(os.listdir(tmp_path / "big")) == ["df_0.png", "df_1.png", "df_32_0.png", "df_32_1.png"]
+    assert Image.open(tmp_path / "big" / "df_32_1.png").size == (32, 32)
