@@ -29,6 +29,16 @@ def load_image_labels(path: str) -> Tuple[List[str], List[str]]:
     return list(files), list(labels)
 
 
+def write_image_labels(folder: str, json_path: str) -> Dict[str, str]:
+    """label_json.py:7-21: image_labels.json for a folder -- every file name of os.listdir(folder) mapped to the text
+    before its FIRST '_' (this file's category rule; decisions use the last-'_' rule of ASR_fast.py:109, and the two
+    differ for labels with underscores such as american_bulldog_1.jpg -> "american"), indent 4."""
+    image_labels = {name: name.split('_')[0] for name in os.listdir(folder)}
+    with open(json_path, 'w') as f:
+        json.dump(image_labels, f, indent=4)
+    return image_labels
+
+
 def list_images(folder: str) -> List[str]:
     """The files compute_asr walks (ASR_fast.py:104-105), sorted for reproducible sharding."""
     return sorted(f for f in os.listdir(folder) if f.lower().endswith(IMAGE_EXTENSIONS))

@@ -149,3 +149,20 @@ def test_iddm_image_writers_equal_reference(golden, tmp_path):
     D.save_one_image_in_images(w["batch"][:2], str(tmp_path / "big"), "df", image_size=32, image_format="png")
     assert sorted(os.listdir(tmp_path / "big")) == ["df_0.png", "df_1.png", "df_32_0.png", "df_32_1.png"]
     assert Image.open(tmp_path / "big" / "df_32_1.png").size == (32, 32)
+
+
+def test_write_image_labels_rule(tmp_path):
+    """label_json.py:12-15 names the category by the text before the FIRST underscore."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import datasets as D
+    d = tmp_path / "figure"
+    d.mkdir()
+    for n in ("american_bulldog_1.jpg", "Abyssinian_7.png", "pug_3.jpg"):
+        (d / n).write_bytes(b"")
+    out = D.write_image_labels(str(d), str(tmp_path / "image_labels.json"))
+    assert out == {"american_bulldog_1.jpg": "american", "Abyssinian_7.png": "Abyssinian", "pug_3.jpg": "pug"}
+    text = (tmp_path / "image_labels.json").read_text()
+    assert json.loads(text) == out and text.startswith('{\n    "')        # indent=4 like the reference writes it
+    files, labels = D.load_image_labels(str(tmp_path / "image_labels.json"))
+    assert dict(zip(files, labels)) == out
+    assert D.label_from_filename("american_bulldog_1.jpg") == "american_bulldog"     # the decision rule differs on purpose
