@@ -266,10 +266,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_start = time.perf_counter()
+
+    def note(what):
+        # progress breadcrumbs on stderr (stdout carries the one JSON line): if a multi-rank run ever stalls, the log
+        # says in which phase and on which rank
+        print(f"[bench rank {rank}/{world} +{time.perf_counter() - t_start:6.1f}s] {what}", file=sys.stderr, flush=True)
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        note("process group up")
     B, S, n = args.batch, args.size, args.ddim_steps
 
     torch.manual_seed(0)
@@ -296,6 +304,7 @@ def main():
     x_T_dev = x_T.to(dev)
     sampler.set_inputs(x_T_dev, clean, fmask, cen, rad)
     torch.cuda.synchronize()
+    note(f"sampler built and captured (pdl={sampler.pdl}), inputs resident")
 
     def exchange():
         # the path's only collective: per-image success flags + ASR counts, once per batch
@@ -330,15 +339,20 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         device_step()
+        if i == 0:
+            torch.cuda.synchronize()
+            note("first trajectory + exchange done")
     clocks = ClockSampler(local)
     ms = timed(device_step, args.steps)
     clk = clocks.stop()
     value = world * B * args.steps / (ms / 1e3)
+    note(f"device-resident leg timed: {ms / args.steps:.1f} ms/step")
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    note(f"end-to-end leg timed: {ms_e2e / args.steps:.1f} ms/step")
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in (x_T, clean, fmask, cen, rad))
     d2h = out_host.numel() * 4
@@ -349,6 +363,7 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         dist.destroy_process_group()
+        note("left the process group")
 
     out = None
     if rank == 0:
@@ -444,6 +459,7 @@ def main():
                                              f"{per_step:.2f} s/step, extrapolated x{n}"}
         done.set()
         guard.cancel()
+        note("untimed profiling / baseline legs done")
         print(json.dumps(out), flush=True)
 
 
