@@ -276,7 +276,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # every collective of this run is a few bytes after minutes of equal work per rank; a rank that waits five
+        # minutes for its peers is stuck, so fail then rather than after the default ten
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
         note("process group up")
     B, S, n = args.batch, args.size, args.ddim_steps
 
