@@ -297,7 +297,7 @@ int advs_ddim_step_composite(const float* x, const float* eps, float* x_out, con
                              const float* radii, const float* feature_mask, int Cm, int blur, float* out, int B,
                              int C, int H, int W, void* stream);
 
-/* ---- IDDM class-conditional UNet + CFG DDIM (model/networks/unet.py:17-128, model/modules/*.py,
+/* ---- IDDM class-conditional UNet + CFG DDIM (model/networks/unet.py:17-128, model/modules/{conv,block,attention}.py,
  *      model/samples/ddim.py:48-100): the bandwidth ops not shared with the diff_model path ------------------ */
 /* nn.MaxPool2d(2) over NHWC (block.py:25) */
 int advs_maxpool2x2(const void* x, void* y, int B, int H, int W, int C, int dtype, void* stream);
