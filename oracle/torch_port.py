@@ -4,8 +4,9 @@ The reference is Python; its heavy arithmetic lives in PyTorch (unpinned; effect
 CPU fp32 in this image).  /root/reference cannot travel to the GPU box, so this file restates the
 algorithm function by function, citing the reference lines it follows.  It is pinned by
 tests/test_oracle_cpu.py against tests/golden/*.pt, which were produced by the UNMODIFIED reference
-(oracle/make_golden.py).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
-`--impl reference` legs may import it; the product never does.
+(oracle/make_golden.py).  Only tests/, __graft_entry__.smoke() and the CPU / PyTorch baseline legs of the
+benchmarks (bench.py's cpu_baseline, `--impl reference`, `--impl torch-gpu`; the `--cpu` column of tools/sweep.py)
+may import it -- always as the thing compared against, never on the measured or shipped path; the package never does.
 
 Parameters are addressed by the reference's state_dict keys.
 """
