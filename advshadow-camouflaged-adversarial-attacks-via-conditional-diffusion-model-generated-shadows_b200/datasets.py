@@ -90,6 +90,29 @@ class ImageMaskLabelDataset(Dataset):
         raise FileNotFoundError("no readable (image, mask) pair in the dataset")
 
 
+class ImageMaskLabelPathDataset(Dataset):
+    """utils/utils_shadow.py:252-276 `CustomDataset` (the IDDM trainer's flavour, ts:417-435): image AND mask are loaded
+    as RGB (torchvision's default_loader), both go through the same transform -- with the trainer's
+    Normalize(0.5, 0.5) the mask therefore arrives as a 3-channel tensor in [-1, 1], which is the `[3,H,W]`
+    feature-mask form apply_shadow accepts -- and the item carries the relative path: (image, mask, label, path).
+    No skipping: a missing file raises, as there."""
+
+    def __init__(self, image_dir, mask_dir, image_paths: Sequence[str], labels: Sequence, transform=None):
+        self.image_dir, self.mask_dir, self.transform = image_dir, mask_dir, transform
+        self.image_paths, self.labels = list(image_paths), list(labels)
+
+    def __len__(self):
+        return len(self.image_paths)
+
+    def __getitem__(self, idx):
+        rel = self.image_paths[idx]
+        image = Image.open(os.path.join(self.image_dir, rel)).convert('RGB')
+        mask = Image.open(os.path.join(self.mask_dir, mask_name(rel))).convert('RGB')
+        if self.transform:
+            image, mask = self.transform(image), self.transform(mask)
+        return image, mask, self.labels[idx], rel
+
+
 def save_images(images, folder: str, names: Sequence[str]):
     """Write [N,3,H,W] tensors in [0,1] as PNG/JPG files named like the inputs (`<label>_<n>.<ext>`), the layout
     compute_asr and classifer_model.py read back."""

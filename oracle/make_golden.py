@@ -536,6 +536,22 @@ def dataset_cases():
         items1 = [ds1[i] for i in (0, 1, 2, 4)]                                                 # (index 3 raises: corrupt file)
         with contextlib.redirect_stdout(io.StringIO()):
             items2 = [ds2[i] for i in range(len(names))]
+    # the IDDM trainer's dataset (utils/utils_shadow.py:252-276), from the source text: RGB masks, same transform, path
+    from torchvision.datasets.folder import default_loader
+    tree = ast.parse(open(os.path.join(R.REF_ROOT, "utils/utils_shadow.py")).read())
+    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "CustomDataset"]
+    ns = {"torch": torch, "os": os, "default_loader": default_loader}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "utils/utils_shadow.py", "exec"), ns)
+    tf3 = transforms.Compose([transforms.Resize((24, 24)), transforms.ToTensor(),
+                              transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "images")), os.makedirs(os.path.join(d, "images_mask"))
+        for n, px, m in zip(names[:2], pixels[:2], masks[:2]):
+            Image.fromarray(px.numpy()).save(os.path.join(d, "images", n))
+            Image.fromarray(m.numpy()).save(os.path.join(d, "images_mask", "mask_" + n))
+        ds3 = ns["CustomDataset"](os.path.join(d, "images"), os.path.join(d, "images_mask"), names[:2], [5, 9], transform=tf3)
+        iddm_items = [dict(zip(("image", "mask", "label", "path"), ds3[i])) for i in range(2)]
+
     # the IDDM generator's writers (utils/utils.py:51-89), from the source text, on a uint8 batch; read back as pixels
     import logging
     import torchvision
@@ -551,7 +567,7 @@ def dataset_cases():
         grid = torch.from_numpy(np.array(Image.open(os.path.join(d, "df.png"))))
         singles = torch.stack([torch.from_numpy(np.array(Image.open(os.path.join(d, f"df_{i}.png")))) for i in range(len(batch))])
     writers = dict(batch=batch, written=written, grid=grid, singles=singles)
-    return dict(names=names, pixels=pixels, masks=masks, files=list(files), labels=list(labels), corrupt=3, no_mask=2, writers=writers,
+    return dict(names=names, pixels=pixels, masks=masks, files=list(files), labels=list(labels), corrupt=3, no_mask=2, writers=writers, iddm_items=iddm_items,
                 main_items=[dict(image=a, label=b) for a, b in items1], main_index=[0, 1, 2, 4],
                 main2_items=[dict(image=a, mask=b, label=c) for a, b, c in items2], len=(len(ds1), len(ds2)))
 

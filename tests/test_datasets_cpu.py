@@ -166,3 +166,27 @@ def test_write_image_labels_rule(tmp_path):
     files, labels = D.load_image_labels(str(tmp_path / "image_labels.json"))
     assert dict(zip(files, labels)) == out
     assert D.label_from_filename("american_bulldog_1.jpg") == "american_bulldog"     # the decision rule differs on purpose
+
+
+def test_iddm_trainer_dataset_equals_reference(golden, tmp_path):
+    """datasets.ImageMaskLabelPathDataset against the reference's own utils/utils_shadow.py:252-276 class (run from the
+    source text): RGB masks through the same Normalize(0.5) transform -> 3-channel masks in [-1, 1], 4-tuples with path."""
+    import advshadow_b200  # noqa: F401
+    from advshadow_b200 import datasets as D
+    from PIL import Image
+    from torchvision import transforms
+    g = golden("datasets.pt")
+    (tmp_path / "images").mkdir(), (tmp_path / "images_mask").mkdir()
+    for n, px, m in zip(g["names"][:2], g["pixels"][:2], g["masks"][:2]):
+        Image.fromarray(px.numpy()).save(str(tmp_path / "images" / n))
+        Image.fromarray(m.numpy()).save(str(tmp_path / "images_mask" / D.mask_name(n)))
+    tf = transforms.Compose([transforms.Resize((24, 24)), transforms.ToTensor(),
+                             transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])
+    ds = D.ImageMaskLabelPathDataset(str(tmp_path / "images"), str(tmp_path / "images_mask"), g["names"][:2], [5, 9], transform=tf)
+    assert len(ds) == 2
+    for i, want in enumerate(g["iddm_items"]):
+        img, mask, lab, path = ds[i]
+        assert torch.equal(img, want["image"]) and torch.equal(mask, want["mask"]) and lab == want["label"] and path == want["path"]
+        assert mask.shape[0] == 3 and float(mask.min()) == -1.0 and float(mask.max()) == 1.0
+    with pytest.raises(OSError):
+        D.ImageMaskLabelPathDataset(str(tmp_path / "images"), str(tmp_path / "images_mask"), ["missing_1.png"], [0])[0]
